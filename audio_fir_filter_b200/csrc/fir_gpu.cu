@@ -1,0 +1,816 @@
+// fir_gpu.cu -- host side of the C-ABI declared in include/fir_gpu.h.
+//
+// Device-memory plan per context (one context per GPU):
+//   d_pcm   interleaved PCM staging (host entry points only; encode reuses it)
+//   d_x     zero-padded planar FP64 input of ONE chunk: [channels][x_pitch],
+//           x_pitch = roundup(chunk_frames + 2H, 16); sample j of the chunk sits
+//           at index j + H.  Bounded (X_BUDGET) so that hour-long multichannel
+//           files stream through it chunk by chunk.
+//   d_y     the PARKED filtered signal, planar FP64 [channels][y_pitch]: it has
+//           to outlive the FIR because the encode gain depends on the global
+//           peak (ProcessFile.cp:92-101), which in sample-block mode is only
+//           known after the cross-GPU max.
+//   d_peak  8 bytes: bit pattern of max|y| (fused into the FIR epilogue)
+// There is no CPU fallback anywhere in this file: every entry point needs a
+// live sm_100 device.
+#include "../../include/fir_gpu.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fir_fp64.cuh"
+#include "pcm_codec.cuh"
+#include "sinc_kernel.cuh"
+
+using namespace firgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+	g_err = msg;
+	return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+	do {                                                                                          \
+		cudaError_t e_ = (expr);                                                                  \
+		if (e_ != cudaSuccess)                                                                    \
+			return fail(e_ == cudaErrorMemoryAllocation ? FIR_GPU_ERR_NOMEM : FIR_GPU_ERR_CUDA,   \
+			            std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+	} while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+// ---- FIR kernel variants ------------------------------------------------------
+
+struct FirVariant {
+	const char* name;
+	int nt, kt, stages, t_out, box_rows, smem;
+	void (*kernel)(const CUtensorMap, const double*, int, double*, long long, long long, unsigned long long*);
+};
+
+template <class Cfg>
+FirVariant make_variant(const char* name)
+{
+	return {name, Cfg::NT, Cfg::KT, Cfg::STAGES, Cfg::T_OUT, Cfg::BOX_ROWS, Cfg::SMEM_BYTES,
+	        fir_fp64_kernel<Cfg>};
+}
+
+constexpr int MAX_KT = 1024; // tap arrays are zero-padded to a multiple of this
+
+const FirVariant* fir_variants(int* n)
+{
+	static const FirVariant v[] = {
+		make_variant<FirCfg<256, 512, 2, 2>>("nt256_kt512_s2_b2"),
+		make_variant<FirCfg<128, 512, 2, 4>>("nt128_kt512_s2_b4"),
+		make_variant<FirCfg<256, 512, 3, 1>>("nt256_kt512_s3_b1"),
+		make_variant<FirCfg<128, 256, 3, 4>>("nt128_kt256_s3_b4"),
+		make_variant<FirCfg<256, 1024, 2, 2>>("nt256_kt1024_s2_b2"),
+		make_variant<FirCfg<64, 512, 2, 8>>("nt64_kt512_s2_b8"),
+	};
+	*n = (int) (sizeof(v) / sizeof(v[0]));
+	return v;
+}
+
+struct EventPair {
+	cudaEvent_t a = nullptr, b = nullptr;
+};
+
+} // namespace
+
+struct fir_gpu_kernel {
+	int device = 0;
+	int64_t n_taps = 0;   // M + 1
+	int64_t n_padded = 0; // multiple of MAX_KT, zero tail
+	double* d_taps = nullptr;
+};
+
+struct fir_gpu_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	PFN_encodeTiled encode_tiled = nullptr;
+
+	unsigned char* d_pcm = nullptr;
+	size_t pcm_cap = 0;
+	double* d_x = nullptr;
+	size_t x_cap = 0;
+	double* d_y = nullptr;
+	size_t y_cap = 0;
+	unsigned long long* d_peak = nullptr;
+	double* d_sink = nullptr;
+
+	bool parked = false;
+	fir_gpu_pcm fmt{};
+	int64_t y_pitch = 0;
+	int variant = 0;
+
+	// timing of the last apply / encode
+	std::vector<EventPair> pool;
+	size_t pool_used = 0;
+	std::vector<size_t> t_h2d, t_decode, t_fir, t_peak, t_encode, t_d2h;
+	int64_t fir_launches = 0, other_launches = 0;
+	int64_t x_budget_bytes = (int64_t) 2 << 30;
+	// cudaFuncSetAttribute is per device: remember what this context's device has
+	bool codec_attr[12] = {};
+	std::vector<char> fir_attr;
+};
+
+namespace {
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev)
+	{
+		cudaGetDevice(&prev);
+		if (prev != dev) cudaSetDevice(dev);
+		else prev = -1;
+	}
+	~DeviceGuard()
+	{
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
+
+int ensure(void** p, size_t* cap, size_t need)
+{
+	if (*cap >= need) return FIR_GPU_OK;
+	if (*p) cudaFree(*p);
+	*p = nullptr;
+	*cap = 0;
+	// grow with a little slack; +64 so codec tails can be staged safely
+	const size_t want = need + need / 16 + 256;
+	cudaError_t e = cudaMalloc(p, want);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		e = cudaMalloc(p, need + 256);
+		if (e != cudaSuccess)
+			return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(need) +
+			                                   " B): " + cudaGetErrorString(e));
+		*cap = need + 256;
+		return FIR_GPU_OK;
+	}
+	*cap = want;
+	return FIR_GPU_OK;
+}
+
+size_t begin_span(fir_gpu_ctx* c)
+{
+	if (c->pool_used == c->pool.size()) {
+		EventPair p;
+		cudaEventCreate(&p.a);
+		cudaEventCreate(&p.b);
+		c->pool.push_back(p);
+	}
+	cudaEventRecord(c->pool[c->pool_used].a, c->stream);
+	return c->pool_used++;
+}
+
+void end_span(fir_gpu_ctx* c, size_t i) { cudaEventRecord(c->pool[i].b, c->stream); }
+
+void reset_timing(fir_gpu_ctx* c, bool all)
+{
+	if (all) {
+		c->pool_used = 0;
+		c->t_h2d.clear();
+		c->t_decode.clear();
+		c->t_fir.clear();
+		c->t_peak.clear();
+		c->fir_launches = 0;
+		c->other_launches = 0;
+		c->t_encode.clear();
+		c->t_d2h.clear();
+	}
+}
+
+double span_ms(fir_gpu_ctx* c, const std::vector<size_t>& v)
+{
+	double tot = 0.0;
+	for (size_t i : v) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, c->pool[i].a, c->pool[i].b) == cudaSuccess) tot += ms;
+	}
+	return tot;
+}
+
+int check_fmt(const fir_gpu_pcm* f)
+{
+	if (!f) return fail(FIR_GPU_ERR_INVALID, "null format");
+	if (f->frames < 0 || f->halo_left < 0 || f->halo_right < 0)
+		return fail(FIR_GPU_ERR_INVALID, "negative frame count");
+	if (f->channels < 1 || f->channels > 256) return fail(FIR_GPU_ERR_INVALID, "channels must be 1..256");
+	if (f->bits != 16 && f->bits != 24 && f->bits != 32)
+		return fail(FIR_GPU_ERR_INVALID, "bits must be 16, 24 or 32");
+	return FIR_GPU_OK;
+}
+
+template <int BITS, bool BE>
+void launch_decode(fir_gpu_ctx* c, const unsigned char* pcm, int64_t avail_lo, int64_t avail_hi, int64_t g0,
+                   int64_t n_x, int ch, double* x, int64_t x_pitch)
+{
+	const int fb = ch * (BITS / 8);
+	const int F = codec_tile_frames(fb);
+	const size_t smem = (size_t) F * fb + 64;
+	bool& attr_done = c->codec_attr[(BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
+	if (!attr_done) {
+		cudaFuncSetAttribute(pcm_decode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+		attr_done = true;
+	}
+	const unsigned blocks = (unsigned) ((n_x + F - 1) / F);
+	pcm_decode_kernel<BITS, BE><<<blocks, CODEC_NT, smem, c->stream>>>(pcm, avail_lo, avail_hi, g0, n_x, ch, x,
+	                                                                   x_pitch);
+}
+
+template <int BITS, bool BE>
+void launch_encode(fir_gpu_ctx* c, const double* y, int64_t y_pitch, int64_t frames, int ch, double gain,
+                   unsigned char* pcm)
+{
+	const int fb = ch * (BITS / 8);
+	const int F = codec_tile_frames(fb);
+	const size_t smem = (size_t) F * fb + 64;
+	bool& attr_done = c->codec_attr[6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
+	if (!attr_done) {
+		cudaFuncSetAttribute(pcm_encode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+		attr_done = true;
+	}
+	const unsigned blocks = (unsigned) ((frames + F - 1) / F);
+	pcm_encode_kernel<BITS, BE><<<blocks, CODEC_NT, smem, c->stream>>>(y, y_pitch, frames, ch, gain, pcm);
+}
+
+#define DISPATCH_CODEC(fn, bits, be, ...)                                  \
+	do {                                                                   \
+		if ((bits) == 16) { if (be) fn<16, true>(__VA_ARGS__); else fn<16, false>(__VA_ARGS__); } \
+		else if ((bits) == 24) { if (be) fn<24, true>(__VA_ARGS__); else fn<24, false>(__VA_ARGS__); } \
+		else { if (be) fn<32, true>(__VA_ARGS__); else fn<32, false>(__VA_ARGS__); } \
+	} while (0)
+
+// One FIR launch over a zero-padded planar chunk resident at d_x.
+int launch_fir(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* d_x, int64_t x_pitch, int ch, double* y,
+               int64_t y_pitch, int64_t frames, unsigned long long* peak)
+{
+	int nv = 0;
+	const FirVariant* vs = fir_variants(&nv);
+	const FirVariant& v = vs[(c->variant >= 0 && c->variant < nv) ? c->variant : 0];
+
+	CUtensorMap map;
+	const cuuint64_t dims[3] = {16, (cuuint64_t) (x_pitch / 16), (cuuint64_t) ch};
+	const cuuint64_t strides[2] = {128, (cuuint64_t) x_pitch * 8};
+	const cuuint32_t box[3] = {16, (cuuint32_t) v.box_rows, 1};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	CUresult r = c->encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) d_x, dims, strides, box, estr,
+	                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+	                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return fail(FIR_GPU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int) r));
+
+	if ((int) c->fir_attr.size() < nv) c->fir_attr.assign(nv, 0);
+	const int vi = (int) (&v - vs);
+	if (!c->fir_attr[vi]) {
+		CU_TRY(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+		c->fir_attr[vi] = 1;
+	}
+	const int n_ktiles = (int) ((k->n_taps + v.kt - 1) / v.kt);
+	dim3 grid((unsigned) ((frames + v.t_out - 1) / v.t_out), (unsigned) ch);
+	v.kernel<<<grid, v.nt, v.smem, c->stream>>>(map, k->d_taps, n_ktiles, y, (long long) y_pitch, (long long) frames,
+	                                           peak);
+	CU_TRY(cudaGetLastError());
+	c->fir_launches++;
+	return FIR_GPU_OK;
+}
+
+int usable_device(int dev, cudaDeviceProp* prop)
+{
+	cudaDeviceProp p;
+	if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	if (prop) *prop = p;
+	return p.major == 10; // sm_100 family only: the cubin is sm_100a
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ life cycle
+
+extern "C" {
+
+int fir_gpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	int ok = 0;
+	for (int d = 0; d < n; ++d) ok += usable_device(d, nullptr);
+	return ok;
+}
+
+const char* fir_gpu_last_error(void) { return g_err.c_str(); }
+
+int fir_gpu_create(int device, fir_gpu_ctx** out)
+{
+	if (!out) return fail(FIR_GPU_ERR_INVALID, "null out");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(FIR_GPU_ERR_NO_DEVICE,
+		            std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+	}
+	if (device < 0 || device >= n) return fail(FIR_GPU_ERR_INVALID, "device index out of range");
+	cudaDeviceProp prop;
+	if (!usable_device(device, &prop))
+		return fail(FIR_GPU_ERR_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
+
+	DeviceGuard g(device);
+	fir_gpu_ctx* c = new fir_gpu_ctx();
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
+	CU_TRY(cudaMalloc(&c->d_peak, 64));
+	CU_TRY(cudaMemset(c->d_peak, 0, 64));
+	CU_TRY(cudaMalloc(&c->d_sink, 8));
+
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qr;
+	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+	if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+		fir_gpu_destroy(c);
+		return fail(FIR_GPU_ERR_NO_DEVICE, "driver lacks cuTensorMapEncodeTiled (TMA)");
+	}
+	c->encode_tiled = (PFN_encodeTiled) fn;
+	*out = c;
+	return FIR_GPU_OK;
+}
+
+void fir_gpu_destroy(fir_gpu_ctx* c)
+{
+	if (!c) return;
+	DeviceGuard g(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto& p : c->pool) {
+		cudaEventDestroy(p.a);
+		cudaEventDestroy(p.b);
+	}
+	cudaFree(c->d_pcm);
+	cudaFree(c->d_x);
+	cudaFree(c->d_y);
+	cudaFree(c->d_peak);
+	cudaFree(c->d_sink);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+}
+
+int fir_gpu_set_stream(fir_gpu_ctx* c, void* s)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	c->stream = s ? (cudaStream_t) s : c->own_stream;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_synchronize(fir_gpu_ctx* c)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	DeviceGuard g(c->device);
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
+void* fir_gpu_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		g_err = "cudaHostAlloc failed";
+		return nullptr;
+	}
+	return p;
+}
+
+void fir_gpu_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+int fir_gpu_set_variant(fir_gpu_ctx* c, int variant)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	int nv = 0;
+	fir_variants(&nv);
+	if (variant < 0 || variant >= nv) return fail(FIR_GPU_ERR_INVALID, "no such FIR variant");
+	c->variant = variant;
+	return FIR_GPU_OK;
+}
+
+// ------------------------------------------------------------ build_kernel
+
+static int alloc_kernel(fir_gpu_ctx* c, int64_t n_taps, fir_gpu_kernel** out)
+{
+	fir_gpu_kernel* k = new fir_gpu_kernel();
+	k->device = c->device;
+	k->n_taps = n_taps;
+	k->n_padded = round_up(n_taps, MAX_KT);
+	cudaError_t e = cudaMalloc(&k->d_taps, (size_t) k->n_padded * sizeof(double));
+	if (e != cudaSuccess) {
+		delete k;
+		return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc taps: ") + cudaGetErrorString(e));
+	}
+	*out = k;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_build_kernel(fir_gpu_ctx* c, double fc_norm, double bw_norm, fir_gpu_kernel** out, int64_t* half_len)
+{
+	if (!c || !out) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	*out = nullptr;
+	if (!(bw_norm > 0.0) || !std::isfinite(bw_norm)) return fail(FIR_GPU_ERR_INVALID, "slope must be > 0");
+	if (!(fc_norm > 0.0) || !(fc_norm < 0.5))
+		return fail(FIR_GPU_ERR_INVALID, "cutoff must lie in (0, sampleRate/2)");
+	// M = round(4/bw), forced even (decision D4)
+	const long double mf = 4.0L / (long double) bw_norm;
+	if (mf > 1.0e9L) return fail(FIR_GPU_ERR_INVALID, "slope too narrow: more than 1e9 taps");
+	int64_t M = (int64_t) llroundl(mf);
+	if (M & 1) ++M;
+	if (M < 2) M = 2;
+
+	DeviceGuard g(c->device);
+	fir_gpu_kernel* k = nullptr;
+	int rc = alloc_kernel(c, M + 1, &k);
+	if (rc) return rc;
+	const int blocks = (int) ((M + 1 + 255) / 256);
+	double* d_lp = nullptr;
+	dd* d_part = nullptr;
+	cudaError_t e = cudaMalloc(&d_lp, (size_t) (M + 1) * sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t) (blocks + 1) * sizeof(dd));
+	if (e != cudaSuccess) {
+		cudaFree(d_lp);
+		fir_gpu_kernel_free(k);
+		return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+	}
+	sinc_lowpass_kernel<<<blocks, 256, 0, c->stream>>>(M, fc_norm, d_lp, d_part);
+	sinc_sum_kernel<<<1, 256, 0, c->stream>>>(d_part, blocks, d_part + blocks);
+	sinc_lowcut_kernel<<<(unsigned) ((k->n_padded + 255) / 256), 256, 0, c->stream>>>(M, d_lp, d_part + blocks,
+	                                                                                 k->d_taps, k->n_padded);
+	e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_lp);
+	cudaFree(d_part);
+	if (e != cudaSuccess) {
+		fir_gpu_kernel_free(k);
+		return fail(FIR_GPU_ERR_CUDA, std::string("build_kernel: ") + cudaGetErrorString(e));
+	}
+	c->other_launches += 3;
+	if (half_len) *half_len = M / 2;
+	*out = k;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_kernel_from_taps(fir_gpu_ctx* c, const double* taps, int64_t n_taps, fir_gpu_kernel** out)
+{
+	if (!c || !out || !taps) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	*out = nullptr;
+	if (n_taps < 1 || !(n_taps & 1)) return fail(FIR_GPU_ERR_INVALID, "tap count must be odd (M even)");
+	DeviceGuard g(c->device);
+	fir_gpu_kernel* k = nullptr;
+	int rc = alloc_kernel(c, n_taps, &k);
+	if (rc) return rc;
+	cudaError_t e = cudaMemcpyAsync(k->d_taps, taps, (size_t) n_taps * sizeof(double), cudaMemcpyHostToDevice,
+	                                c->stream);
+	if (e == cudaSuccess && k->n_padded > n_taps) {
+		pad_taps_kernel<<<(unsigned) ((k->n_padded - n_taps + 255) / 256), 256, 0, c->stream>>>(k->d_taps, n_taps,
+		                                                                                       k->n_padded);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e != cudaSuccess) {
+		fir_gpu_kernel_free(k);
+		return fail(FIR_GPU_ERR_CUDA, std::string("kernel_from_taps: ") + cudaGetErrorString(e));
+	}
+	*out = k;
+	return FIR_GPU_OK;
+}
+
+int64_t fir_gpu_kernel_num_taps(const fir_gpu_kernel* k) { return k ? k->n_taps : 0; }
+
+int fir_gpu_kernel_taps(fir_gpu_ctx* c, const fir_gpu_kernel* k, double* taps_out, int64_t n)
+{
+	if (!c || !k || !taps_out) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (n != k->n_taps) return fail(FIR_GPU_ERR_INVALID, "tap count mismatch");
+	DeviceGuard g(c->device);
+	CU_TRY(cudaMemcpyAsync(taps_out, k->d_taps, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
+void fir_gpu_kernel_free(fir_gpu_kernel* k)
+{
+	if (!k) return;
+	DeviceGuard g(k->device);
+	cudaFree(k->d_taps);
+	delete k;
+}
+
+// ------------------------------------------------------------------- apply
+
+static int apply_dev_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_dev, const fir_gpu_pcm* fmt)
+{
+	int rc = check_fmt(fmt);
+	if (rc) return rc;
+	if (!pcm_dev && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
+	if (k->device != c->device) return fail(FIR_GPU_ERR_STATE, "kernel lives on another device");
+	DeviceGuard g(c->device);
+
+	const int64_t H = (k->n_taps - 1) / 2;
+	const int ch = fmt->channels;
+	const int64_t frames = fmt->frames;
+	c->parked = false;
+	c->fmt = *fmt;
+	c->y_pitch = round_up(std::max<int64_t>(frames, 1), 16);
+	rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * ch * sizeof(double));
+	if (rc) return rc;
+	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
+
+	// chunk so that the decoded FP64 input stays within x_budget_bytes
+	int nv = 0;
+	const FirVariant* vs = fir_variants(&nv);
+	const int t_out = vs[c->variant].t_out;
+	int64_t chunk = c->x_budget_bytes / 8 / ch - 2 * H - 16;
+	chunk = chunk / t_out * t_out;
+	if (chunk < t_out) chunk = t_out;
+	if (chunk > frames) chunk = frames;
+
+	const int64_t avail_lo = -fmt->halo_left, avail_hi = frames + fmt->halo_right;
+	for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
+		const int64_t nf = std::min(chunk, frames - f0);
+		const int64_t x_pitch = round_up(nf + 2 * H, 16);
+		rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
+		if (rc) return rc;
+		size_t s = begin_span(c);
+		DISPATCH_CODEC(launch_decode, fmt->bits, fmt->big_endian != 0, c, (const unsigned char*) pcm_dev, avail_lo,
+		               avail_hi, f0 - H, x_pitch, ch, c->d_x, x_pitch);
+		end_span(c, s);
+		c->t_decode.push_back(s);
+		c->other_launches++;
+		CU_TRY(cudaGetLastError());
+		s = begin_span(c);
+		rc = launch_fir(c, k, c->d_x, x_pitch, ch, c->d_y + f0, c->y_pitch, nf, c->d_peak);
+		end_span(c, s);
+		c->t_fir.push_back(s);
+		if (rc) return rc;
+	}
+	c->parked = true;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host, const fir_gpu_pcm* fmt)
+{
+	if (!c || !k) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	int rc = check_fmt(fmt);
+	if (rc) return rc;
+	if (!pcm_host && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
+	DeviceGuard g(c->device);
+	reset_timing(c, true);
+	const size_t fb = (size_t) fmt->channels * (fmt->bits / 8);
+	const size_t in_bytes = (size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fb;
+	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, in_bytes + 32);
+	if (rc) return rc;
+	size_t s = begin_span(c);
+	if (in_bytes) CU_TRY(cudaMemcpyAsync(c->d_pcm, pcm_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+	end_span(c, s);
+	c->t_h2d.push_back(s);
+	return apply_dev_impl(c, k, c->d_pcm, fmt);
+}
+
+int fir_gpu_apply_dev(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_dev, const fir_gpu_pcm* fmt)
+{
+	if (!c || !k) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	reset_timing(c, true);
+	return apply_dev_impl(c, k, pcm_dev, fmt);
+}
+
+int fir_gpu_filter_f64(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* x_host, int64_t frames,
+                       int32_t channels, double* y_host)
+{
+	if (!c || !k || !x_host || !y_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (frames < 1 || channels < 1 || channels > 65535) return fail(FIR_GPU_ERR_INVALID, "bad shape");
+	if (k->device != c->device) return fail(FIR_GPU_ERR_STATE, "kernel lives on another device");
+	DeviceGuard g(c->device);
+	reset_timing(c, true);
+	const int64_t H = (k->n_taps - 1) / 2;
+	const int64_t x_pitch = round_up(frames + 2 * H, 16);
+	c->parked = false;
+	c->y_pitch = round_up(frames, 16);
+	int rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * channels * sizeof(double));
+	if (!rc) rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * channels * sizeof(double));
+	if (rc) return rc;
+	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
+	CU_TRY(cudaMemsetAsync(c->d_x, 0, (size_t) x_pitch * channels * sizeof(double), c->stream));
+	CU_TRY(cudaMemcpy2DAsync(c->d_x + H, (size_t) x_pitch * 8, x_host, (size_t) frames * 8, (size_t) frames * 8,
+	                         (size_t) channels, cudaMemcpyHostToDevice, c->stream));
+	size_t s = begin_span(c);
+	rc = launch_fir(c, k, c->d_x, x_pitch, channels, c->d_y, c->y_pitch, frames, c->d_peak);
+	end_span(c, s);
+	c->t_fir.push_back(s);
+	if (rc) return rc;
+	CU_TRY(cudaMemcpy2DAsync(y_host, (size_t) frames * 8, c->d_y, (size_t) c->y_pitch * 8, (size_t) frames * 8,
+	                         (size_t) channels, cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	// leave the signal parked so fir_gpu_peak / fir_gpu_parked work on it
+	c->fmt = fir_gpu_pcm{frames, channels, 0, 0, 0, 0};
+	c->parked = true;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_parked(fir_gpu_ctx* c, double* y_host, int64_t frames, int32_t channels)
+{
+	if (!c || !y_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on this context");
+	if (frames != c->fmt.frames || channels != c->fmt.channels)
+		return fail(FIR_GPU_ERR_INVALID, "shape does not match the parked signal");
+	DeviceGuard g(c->device);
+	if (frames)
+		CU_TRY(cudaMemcpy2DAsync(y_host, (size_t) frames * 8, c->d_y, (size_t) c->y_pitch * 8, (size_t) frames * 8,
+		                         (size_t) channels, cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
+// -------------------------------------------------------------------- peak
+
+int fir_gpu_peak(fir_gpu_ctx* c, double* peak)
+{
+	if (!c || !peak) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on this context");
+	DeviceGuard g(c->device);
+	unsigned long long bits = 0;
+	CU_TRY(cudaMemcpyAsync(&bits, c->d_peak, 8, cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	std::memcpy(peak, &bits, 8);
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_peak_dev(fir_gpu_ctx* c, void** peak_dev)
+{
+	if (!c || !peak_dev) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on this context");
+	*peak_dev = c->d_peak;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_peak_recompute(fir_gpu_ctx* c, double* peak)
+{
+	if (!c || !peak) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on this context");
+	DeviceGuard g(c->device);
+	unsigned long long* d_tmp = c->d_peak + 1; // second slot of the 64-byte scratch
+	CU_TRY(cudaMemsetAsync(d_tmp, 0, 8, c->stream));
+	if (c->fmt.frames > 0) {
+		const int64_t pairs = c->fmt.frames / 2;
+		unsigned bx = (unsigned) std::min<int64_t>((pairs + 255) / 256, (int64_t) c->sm_count * 8);
+		if (bx < 1) bx = 1;
+		size_t s = begin_span(c);
+		peak_abs_kernel<<<dim3(bx, (unsigned) c->fmt.channels), 256, 0, c->stream>>>(c->d_y, c->y_pitch,
+		                                                                            c->fmt.frames, d_tmp);
+		end_span(c, s);
+		c->t_peak.push_back(s);
+		c->other_launches++;
+		CU_TRY(cudaGetLastError());
+	}
+	unsigned long long bits = 0;
+	CU_TRY(cudaMemcpyAsync(&bits, d_tmp, 8, cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	std::memcpy(peak, &bits, 8);
+	return FIR_GPU_OK;
+}
+
+// ------------------------------------------------------------------ encode
+
+int fir_gpu_encode_dev(fir_gpu_ctx* c, double scale, void* pcm_dev)
+{
+	if (!c || !pcm_dev) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked || c->fmt.bits == 0) return fail(FIR_GPU_ERR_STATE, "no PCM-format signal is parked on this context");
+	if (!(scale > 0.0) || !std::isfinite(scale)) return fail(FIR_GPU_ERR_INVALID, "scale must be finite and > 0");
+	DeviceGuard g(c->device);
+	if (c->fmt.frames == 0) return FIR_GPU_OK;
+	const double gain = scale * std::ldexp(1.0, c->fmt.bits - 1);
+	size_t s = begin_span(c);
+	DISPATCH_CODEC(launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->d_y, c->y_pitch, c->fmt.frames,
+	               c->fmt.channels, gain, (unsigned char*) pcm_dev);
+	end_span(c, s);
+	c->t_encode.push_back(s);
+	c->other_launches++;
+	CU_TRY(cudaGetLastError());
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_encode(fir_gpu_ctx* c, double scale, void* pcm_host)
+{
+	if (!c || !pcm_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked || c->fmt.bits == 0) return fail(FIR_GPU_ERR_STATE, "no PCM-format signal is parked on this context");
+	DeviceGuard g(c->device);
+	const size_t out_bytes = (size_t) c->fmt.frames * c->fmt.channels * (c->fmt.bits / 8);
+	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, out_bytes + 32);
+	if (rc) return rc;
+	rc = fir_gpu_encode_dev(c, scale, c->d_pcm);
+	if (rc) return rc;
+	size_t s = begin_span(c);
+	if (out_bytes) CU_TRY(cudaMemcpyAsync(pcm_host, c->d_pcm, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+	end_span(c, s);
+	c->t_d2h.push_back(s);
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
+// ------------------------------------------------- measurement and synthesis
+
+int fir_gpu_last_timing(fir_gpu_ctx* c, fir_gpu_timing* t)
+{
+	if (!c || !t) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	DeviceGuard g(c->device);
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	t->h2d_ms = span_ms(c, c->t_h2d);
+	t->decode_ms = span_ms(c, c->t_decode);
+	t->fir_ms = span_ms(c, c->t_fir);
+	t->peak_ms = span_ms(c, c->t_peak);
+	t->encode_ms = span_ms(c, c->t_encode);
+	t->d2h_ms = span_ms(c, c->t_d2h);
+	t->fir_launches = c->fir_launches;
+	t->other_launches = c->other_launches;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_synth_pcm_dev(fir_gpu_ctx* c, uint64_t seed, int64_t first_frame, int64_t frames, int32_t channels,
+                          int32_t bits, int32_t big_endian, int64_t rate, double gain, void* pcm_dev)
+{
+	if (!c || !pcm_dev) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (bits != 16 && bits != 24 && bits != 32) return fail(FIR_GPU_ERR_INVALID, "bits must be 16, 24 or 32");
+	if (frames < 0 || channels < 1 || rate < 1) return fail(FIR_GPU_ERR_INVALID, "bad shape");
+	DeviceGuard g(c->device);
+	if (frames == 0) return FIR_GPU_OK;
+	const int64_t total = frames * channels;
+	const unsigned blocks = (unsigned) std::min<int64_t>((total + 255) / 256, (int64_t) c->sm_count * 16);
+	synth_pcm_kernel<<<blocks, 256, 0, c->stream>>>(seed, first_frame, frames, channels, bits, big_endian, rate, gain,
+	                                               (unsigned char*) pcm_dev);
+	CU_TRY(cudaGetLastError());
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_fp64_peak(fir_gpu_ctx* c, int kind, double seconds, double* tflops)
+{
+	if (!c || !tflops) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (kind != 0 && kind != 1) return fail(FIR_GPU_ERR_INVALID, "kind must be 0 (DFMA) or 1 (DMMA)");
+	DeviceGuard g(c->device);
+	const int blocks = c->sm_count * 8, threads = 256;
+	cudaEvent_t a, b;
+	CU_TRY(cudaEventCreate(&a));
+	CU_TRY(cudaEventCreate(&b));
+	auto run = [&](int iters) -> double {
+		cudaEventRecord(a, c->stream);
+		if (kind == 0) dfma_probe_kernel<<<blocks, threads, 0, c->stream>>>(1.0000001, 1e-9, iters, c->d_sink);
+		else dmma_probe_kernel<<<blocks, threads, 0, c->stream>>>(1.0000001, 1e-9, iters, c->d_sink);
+		cudaEventRecord(b, c->stream);
+		cudaEventSynchronize(b);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, a, b);
+		return (double) ms * 1e-3;
+	};
+	// flop per loop trip for the whole grid
+	const double per_iter = kind == 0 ? 2.0 * blocks * threads * 16 * 8
+	                                  : 512.0 * 8 * 4 * (double) (blocks * (threads / 32));
+	run(64); // warm-up
+	int iters = 4096;
+	double t = run(iters);
+	if (seconds > 0 && t > 0) {
+		double want = seconds / t * iters;
+		if (want > 2.0e9) want = 2.0e9;
+		if (want > iters) {
+			iters = (int) want;
+			t = run(iters);
+		}
+	}
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	CU_TRY(cudaGetLastError());
+	*tflops = per_iter * iters / t * 1e-12;
+	return FIR_GPU_OK;
+}
+
+} // extern "C"

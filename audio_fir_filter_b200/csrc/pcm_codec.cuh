@@ -1,0 +1,248 @@
+// pcm_codec.cuh -- the HBM-bound kernels either side of the FIR:
+//   pcm_decode_kernel : AudioSamples::readAll()            (reference ProcessFile.cp:40-41)
+//   peak_abs_kernel   : VectorMath::max_mag() loop         (reference ProcessFile.cp:92-96)
+//   pcm_encode_kernel : AudioSamples::normalize + writeAll (reference ProcessFile.cp:100,117)
+//   synth_pcm_kernel  : counter-based synthetic PCM, mirrors
+//                       oracle_synth_sample() operation for operation.
+// Conventions (decision D2): x = int / 2^(bits-1);
+// q = clamp(rint(y * scale * 2^(bits-1))), ties to even, no dither.
+//
+// Both codec kernels move the interleaved bytes with 128-bit coalesced global
+// accesses through a shared-memory tile and touch the planar FP64 side with
+// lane == consecutive frame, so every global transaction is a full sector.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace firgpu {
+
+constexpr int CODEC_NT = 256;
+constexpr int CODEC_TILE_BYTES = 32768; // interleaved bytes staged per CTA
+
+// frames per CTA tile for a frame of `fb` bytes: a multiple of 32 so a warp
+// never straddles two channels in the planar pass.
+__host__ __device__ inline int codec_tile_frames(int fb)
+{
+	int f = (CODEC_TILE_BYTES / fb) & ~31;
+	return f < 32 ? 32 : f;
+}
+
+// 4 bytes at an arbitrary byte offset of a word-aligned smem tile, packed
+// little-endian (byte at `off` in bits 0..7).
+__device__ __forceinline__ uint32_t lds_unaligned_u32(const uint32_t* tile, uint32_t off)
+{
+	const uint32_t w = off >> 2;
+	const uint32_t lo = tile[w];
+	const uint32_t hi = tile[w + 1];
+	return __funnelshift_r(lo, hi, (off & 3u) << 3);
+}
+
+template <int BITS, bool BE>
+__device__ __forceinline__ int32_t pcm_to_int(uint32_t u)
+{
+	if (BITS == 16) {
+		const uint32_t v = BE ? __byte_perm(u, 0, 0x4401) : (u & 0xffffu);
+		return (int32_t) (int16_t) v;
+	} else if (BITS == 24) {
+		const uint32_t v = BE ? __byte_perm(u, 0, 0x4012) : (u & 0xffffffu);
+		return ((int32_t) (v << 8)) >> 8;
+	} else {
+		return (int32_t) (BE ? __byte_perm(u, 0, 0x0123) : u);
+	}
+}
+
+template <int BITS, bool BE>
+__device__ __forceinline__ uint32_t int_to_pcm(int32_t q)
+{
+	const uint32_t u = (uint32_t) q;
+	if (BITS == 16) return BE ? __byte_perm(u, 0, 0x4401) : (u & 0xffffu);
+	if (BITS == 24) return BE ? __byte_perm(u, 0, 0x4012) : (u & 0xffffffu);
+	return BE ? __byte_perm(u, 0, 0x0123) : u;
+}
+
+// Decode a window of the interleaved PCM into the zero-padded planar layout.
+//   pcm            : first byte of logical frame avail_lo
+//   [avail_lo, avail_hi) : logical frames present in pcm (real data)
+//   g0             : logical frame that lands at x index 0  (= first output frame - H)
+//   n_x            : x entries to write per channel (the whole pitch: zeros
+//                    wherever the logical frame is not available)
+template <int BITS, bool BE>
+__global__ void __launch_bounds__(CODEC_NT)
+pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, long long avail_hi,
+                  long long g0, long long n_x, int channels, double* __restrict__ x, long long x_pitch)
+{
+	constexpr int NB = BITS / 8;
+	extern __shared__ __align__(16) unsigned char tile[];
+	const int fb = channels * NB;
+	const int F = codec_tile_frames(fb);
+	const long long i0 = (long long) blockIdx.x * F;
+
+	// logical frames of this tile that exist in pcm
+	long long ga = g0 + i0, gb = ga + F;
+	if (gb > g0 + n_x) gb = g0 + n_x;
+	if (ga < avail_lo) ga = avail_lo;
+	if (gb > avail_hi) gb = avail_hi;
+	uint32_t mis = 0;
+	if (gb > ga) {
+		const unsigned char* p0 = pcm + (size_t) (ga - avail_lo) * fb;
+		const uint32_t nbytes = (uint32_t) (gb - ga) * fb;
+		mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
+		const unsigned char* base = p0 - mis; // 16-byte aligned
+		const uint32_t end = mis + nbytes;
+		const uint32_t nvec = (end + 15u) >> 4;
+		for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
+			const uint32_t lo = v << 4, hi = lo + 16;
+			if (lo >= mis && hi <= end) {
+				reinterpret_cast<uint4*>(tile)[v] = __ldg(reinterpret_cast<const uint4*>(base + lo));
+			} else { // ragged head / tail: never touch bytes outside the payload
+				const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
+				for (uint32_t s = lo; s < hi; ++s) tile[s] = (s >= a && s < b) ? base[s] : 0;
+			}
+		}
+	}
+	__syncthreads();
+
+	const double inv = 1.0 / (double) (1ll << (BITS - 1));
+	const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+	const int total = F * channels;
+	for (int idx = threadIdx.x; idx < total; idx += CODEC_NT) {
+		const int c = idx / F, fl = idx - c * F;
+		const long long i = i0 + fl;
+		if (i >= n_x) continue;
+		const long long g = g0 + i;
+		double v = 0.0;
+		if (g >= ga && g < gb) {
+			const uint32_t off = mis + (uint32_t) (g - ga) * fb + c * NB;
+			v = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, off)) * inv;
+		}
+		x[(long long) c * x_pitch + i] = v;
+	}
+}
+
+// Planar FP64 -> interleaved PCM.  gain = scale * 2^(bits-1) (one rounding, on
+// the host); the product y*gain is rounded to binary64, then to the nearest
+// integer with ties to even (cvt.rni), after clamping to the signed range.
+template <int BITS, bool BE>
+__global__ void __launch_bounds__(CODEC_NT)
+pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long frames, int channels,
+                  double gain, unsigned char* __restrict__ pcm)
+{
+	constexpr int NB = BITS / 8;
+	extern __shared__ __align__(16) unsigned char tile[];
+	const int fb = channels * NB;
+	const int F = codec_tile_frames(fb);
+	const long long f0 = (long long) blockIdx.x * F;
+	long long f1 = f0 + F;
+	if (f1 > frames) f1 = frames;
+	const int nf = (int) (f1 - f0);
+
+	unsigned char* p0 = pcm + (size_t) f0 * fb;
+	const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
+	const double hi_lim = (double) ((1ll << (BITS - 1)) - 1), lo_lim = -(double) (1ll << (BITS - 1));
+
+	const int total = F * channels;
+	for (int idx = threadIdx.x; idx < total; idx += CODEC_NT) {
+		const int c = idx / F, fl = idx - c * F;
+		if (fl >= nf) continue;
+		double v = y[(long long) c * y_pitch + f0 + fl] * gain;
+		v = fmin(fmax(v, lo_lim), hi_lim);
+		const uint32_t u = int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v));
+		unsigned char* d = tile + mis + (uint32_t) fl * fb + c * NB;
+#pragma unroll
+		for (int b = 0; b < NB; ++b) d[b] = (unsigned char) (u >> (8 * b));
+	}
+	__syncthreads();
+
+	unsigned char* base = p0 - mis;
+	const uint32_t end = mis + (uint32_t) nf * fb;
+	const uint32_t nvec = (end + 15u) >> 4;
+	for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
+		const uint32_t lo = v << 4, hi = lo + 16;
+		if (lo >= mis && hi <= end) {
+			*reinterpret_cast<uint4*>(base + lo) = reinterpret_cast<const uint4*>(tile)[v];
+		} else {
+			const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
+			for (uint32_t s = a; s < b; ++s) base[s] = tile[s];
+		}
+	}
+}
+
+// Stand-alone peak: grid (blocks, channels); 128-bit loads, warp shuffle max,
+// one atomicMax per warp.
+__global__ void __launch_bounds__(256)
+peak_abs_kernel(const double* __restrict__ y, long long y_pitch, long long frames,
+                unsigned long long* __restrict__ peak)
+{
+	const double* yc = y + (long long) blockIdx.y * y_pitch;
+	const long long pairs = frames >> 1;
+	double m = 0.0;
+	for (long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < pairs;
+	     p += (long long) gridDim.x * blockDim.x) {
+		const double2 v = __ldg(reinterpret_cast<const double2*>(yc) + p);
+		m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+	}
+	if ((frames & 1) && blockIdx.x == 0 && threadIdx.x == 0) m = fmax(m, fabs(yc[frames - 1]));
+	m = warp_max(m);
+	if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(peak, (unsigned long long) __double_as_longlong(m));
+}
+
+// ---- synthetic PCM ----------------------------------------------------------
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double synth_tri(long long n, long long period)
+{
+	const long long p = n % period, half = period / 2;
+	const long long v = p < half ? p : period - p;
+	return __ddiv_rn((double) (4 * v - 2 * half), (double) (2 * half));
+}
+
+// Explicit _rn intrinsics: no FMA contraction, so the integers equal the
+// oracle's (compiled with -ffp-contract=off) bit for bit.
+__device__ __forceinline__ long long synth_sample(unsigned long long seed, int channel, long long frame,
+                                                  int bits, long long rate, double gain)
+{
+	const double fs = (double) (1ll << (bits - 1));
+	const unsigned long long r =
+		splitmix64(seed ^ splitmix64(((unsigned long long) channel << 48) ^ (unsigned long long) frame));
+	const double noise =
+		__dsub_rn(__dmul_rn(__dmul_rn((double) (r >> 11), 1.0 / 9007199254740992.0), 2.0), 1.0);
+	long long p_rumble = rate / 5;
+	if (p_rumble < 2) p_rumble = 2;
+	long long p_tone = rate / 1000;
+	if (p_tone < 2) p_tone = 2;
+	double v = __dadd_rn(0.05, __dmul_rn(0.2, synth_tri(frame + 17 * channel, p_rumble)));
+	v = __dadd_rn(v, __dmul_rn(0.3, synth_tri(frame + 5 * channel, p_tone)));
+	v = __dadd_rn(v, __dmul_rn(0.1, noise));
+	v = __dmul_rn(v, gain);
+	double q = rint(__dmul_rn(v, fs));
+	if (q < -fs) q = -fs;
+	if (q > fs - 1.0) q = fs - 1.0;
+	return (long long) q;
+}
+
+__global__ void __launch_bounds__(256)
+synth_pcm_kernel(unsigned long long seed, long long first_frame, long long frames, int channels, int bits,
+                 int big_endian, long long rate, double gain, unsigned char* __restrict__ pcm)
+{
+	const int nb = bits / 8;
+	const long long total = frames * channels;
+	for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total;
+	     s += (long long) gridDim.x * blockDim.x) {
+		const long long f = s / channels;
+		const int c = (int) (s - f * channels);
+		uint32_t u = (uint32_t) synth_sample(seed, c, first_frame + f, bits, rate, gain);
+		unsigned char* d = pcm + (size_t) s * nb;
+		if (big_endian)
+			for (int b = nb - 1; b >= 0; --b) { d[b] = (unsigned char) u; u >>= 8; }
+		else
+			for (int b = 0; b < nb; ++b) { d[b] = (unsigned char) u; u >>= 8; }
+	}
+}
+
+} // namespace firgpu

@@ -1,0 +1,184 @@
+/*
+ * fir_gpu.h -- C-ABI of the B200 (sm_100a) low-cut FIR hot path.
+ *
+ * This is the drop-in boundary for the arithmetic half of the reference's
+ * process_file() (diskerror/audio-fir-filter, ProcessFile.cp:27-120).  The
+ * reference has no FFI of its own; the seam is cut where process_file hands
+ * work to the un-vendored c_lib, and every entry point below names the
+ * reference call site it replaces.  A host that keeps the reference's CLI and
+ * chunk-preserving file I/O calls, per file:
+ *
+ *     fir_gpu_build_kernel   <- WindowedSinc<float64_t>(fc,bw) + makeLowCut()   ProcessFile.cp:48-50
+ *     fir_gpu_apply          <- readAll() + the per-channel thread fan-out over  ProcessFile.cp:41,57-87
+ *                               apply_filter_range()                             FilterCore.h:20-79
+ *     fir_gpu_peak           <- the max_mag() loop                               ProcessFile.cp:92-96
+ *     [host: scale rule  maxMag > 1 || normalize                                 ProcessFile.cp:98]
+ *     fir_gpu_encode         <- AudioSamples::normalize + writeAll(buf, true)    ProcessFile.cp:100,117
+ *
+ * Plain C: opaque handles, plain pointers and sizes, int status codes (0 = ok),
+ * no exceptions across the boundary, no CPU fallback -- without a usable
+ * sm_100 device every call fails with FIR_GPU_ERR_NO_DEVICE.
+ *
+ * Threading: one context per GPU, used by one host thread at a time (the
+ * reference's -t fan-out is replaced by the device grid).  All work of a context
+ * is ordered on one CUDA stream (its own, or the one given to
+ * fir_gpu_set_stream).
+ */
+#ifndef FIR_GPU_H
+#define FIR_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FIR_GPU_API __attribute__((visibility("default")))
+#else
+#define FIR_GPU_API
+#endif
+
+typedef struct fir_gpu_ctx fir_gpu_ctx;       /* per-device state: stream, parked signal, scratch */
+typedef struct fir_gpu_kernel fir_gpu_kernel; /* one tap array resident in HBM */
+
+enum {
+	FIR_GPU_OK = 0,
+	FIR_GPU_ERR_NO_DEVICE = 1, /* no CUDA device / not sm_100 / driver missing */
+	FIR_GPU_ERR_INVALID = 2,   /* bad argument */
+	FIR_GPU_ERR_CUDA = 3,      /* a CUDA call failed; see fir_gpu_last_error() */
+	FIR_GPU_ERR_STATE = 4,     /* call order: nothing parked, wrong context, ... */
+	FIR_GPU_ERR_NOMEM = 5
+};
+
+/* PCM layout of one block of interleaved frames (what AudioFormat tells the
+ * reference: channels(), bits, endianness; ProcessFile.cp:35,43). */
+typedef struct fir_gpu_pcm {
+	int64_t frames;     /* frames to PRODUCE (the block this call owns) */
+	int32_t channels;   /* >= 1 */
+	int32_t bits;       /* 16, 24 or 32, signed two's complement */
+	int32_t big_endian; /* 0 = WAVE order, 1 = AIFF order */
+	/* Sample-block sharding (single long file across GPUs): real frames that
+	 * precede / follow the block in the buffer handed to fir_gpu_apply.  Each is
+	 * at most half_len (more is accepted and ignored); whatever is missing is
+	 * implicit zero, i.e. a true file edge (FilterCore.h:57-61,72-76). */
+	int64_t halo_left;
+	int64_t halo_right;
+} fir_gpu_pcm;
+
+/* Per-phase device times of the last apply/encode on this context, measured
+ * with CUDA events on the context's stream (milliseconds). */
+typedef struct fir_gpu_timing {
+	double h2d_ms, decode_ms, fir_ms, peak_ms, encode_ms, d2h_ms;
+	int64_t fir_launches, other_launches; /* kernels launched by the last apply + encode */
+} fir_gpu_timing;
+
+/* ---- life cycle ---------------------------------------------------------- */
+
+/* Number of usable sm_100 devices (0 when there is none; never a CPU path). */
+FIR_GPU_API int fir_gpu_device_count(void);
+
+FIR_GPU_API int fir_gpu_create(int device, fir_gpu_ctx **out);
+FIR_GPU_API void fir_gpu_destroy(fir_gpu_ctx *ctx);
+
+/* Message of the last failure on the calling thread ("" if none). */
+FIR_GPU_API const char *fir_gpu_last_error(void);
+
+/* Order this context's work on an existing cudaStream_t (e.g. the caller's
+ * framework stream).  NULL restores the context's own stream. */
+FIR_GPU_API int fir_gpu_set_stream(fir_gpu_ctx *ctx, void *cuda_stream);
+FIR_GPU_API int fir_gpu_synchronize(fir_gpu_ctx *ctx);
+
+/* Pinned host memory for the PCM payload buffers (optional; pageable works). */
+FIR_GPU_API void *fir_gpu_host_alloc(size_t bytes);
+FIR_GPU_API void fir_gpu_host_free(void *p);
+
+/* ---- fir_gpu_build_kernel  (ProcessFile.cp:48-50) ------------------------ */
+
+/* Blackman windowed-sinc low-pass of order M = round(4/bw) forced even,
+ * normalised to unity DC gain with a double-double sum, then spectrally
+ * inverted to the low-cut.  fc_norm = freq / sampleRate and bw_norm = slope /
+ * sampleRate, exactly the two arguments at ProcessFile.cp:49.  *half_len
+ * receives M/2 (WindowedSinc::getMo2(), FilterCore.h:29). */
+FIR_GPU_API int fir_gpu_build_kernel(fir_gpu_ctx *ctx, double fc_norm, double bw_norm,
+                                     fir_gpu_kernel **out, int64_t *half_len);
+
+/* A kernel from caller-supplied taps (n_taps odd): for parity tests that must
+ * feed the device the oracle's exact taps. */
+FIR_GPU_API int fir_gpu_kernel_from_taps(fir_gpu_ctx *ctx, const double *taps, int64_t n_taps,
+                                         fir_gpu_kernel **out);
+
+FIR_GPU_API int64_t fir_gpu_kernel_num_taps(const fir_gpu_kernel *k);
+/* Copy the M+1 taps back to the host (parity checks). */
+FIR_GPU_API int fir_gpu_kernel_taps(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, double *taps_out,
+                                    int64_t n);
+FIR_GPU_API void fir_gpu_kernel_free(fir_gpu_kernel *k);
+
+/* ---- fir_gpu_apply  (ProcessFile.cp:41,57-87 / FilterCore.h:20-79) ------- */
+
+/* Filter phase.  pcm_host points at the first byte of frame (-halo_left): the
+ * buffer holds halo_left + frames + halo_right interleaved frames.  Uploads,
+ * decodes to planar FP64, runs
+ *     y[n] = sum_{k=0..M} h[k] * x[n - M/2 + k],  x = 0 outside the file,
+ * for every channel and n in [0, frames), and PARKS y (FP64) in HBM together
+ * with its peak magnitude.  Asynchronous on the context's stream. */
+FIR_GPU_API int fir_gpu_apply(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const void *pcm_host,
+                              const fir_gpu_pcm *fmt);
+
+/* Same with the PCM already resident in device memory (no H2D). */
+FIR_GPU_API int fir_gpu_apply_dev(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const void *pcm_dev,
+                                  const fir_gpu_pcm *fmt);
+
+/* The bare FIR on caller-supplied planar FP64 host samples x[channels][frames]
+ * -> y[channels][frames] (host), bypassing the PCM codec.  This is the
+ * apply_filter_range() equivalent the 1e-12 parity tests call. */
+FIR_GPU_API int fir_gpu_filter_f64(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const double *x_host,
+                                   int64_t frames, int32_t channels, double *y_host);
+
+/* Copy the parked FP64 signal, planar [channels][frames], to the host. */
+FIR_GPU_API int fir_gpu_parked(fir_gpu_ctx *ctx, double *y_host, int64_t frames, int32_t channels);
+
+/* ---- fir_gpu_peak  (ProcessFile.cp:92-96) -------------------------------- */
+
+/* max over channels and frames of |y| of the parked signal on THIS device.
+ * Synchronises the stream.  In sample-block mode the caller max-reduces the
+ * per-device values (NCCL allreduce-max) before choosing the scale. */
+FIR_GPU_API int fir_gpu_peak(fir_gpu_ctx *ctx, double *peak);
+/* Device address of that FP64 scalar (valid until the next apply), so the
+ * all-reduce can run on it without a host round trip. */
+FIR_GPU_API int fir_gpu_peak_dev(fir_gpu_ctx *ctx, void **peak_dev);
+/* Recompute the peak from the parked signal with the stand-alone warp-reduced
+ * kernel instead of the value fused into the FIR epilogue. */
+FIR_GPU_API int fir_gpu_peak_recompute(fir_gpu_ctx *ctx, double *peak);
+
+/* ---- fir_gpu_encode  (ProcessFile.cp:100,117) ---------------------------- */
+
+/* Encode phase: q = clamp(rint(y * scale * 2^(bits-1))) (ties to even, clamp to
+ * the signed range, no dither), interleave, endian as in the matching apply;
+ * writes frames*channels*bits/8 bytes to pcm_host.  Synchronous on return. */
+FIR_GPU_API int fir_gpu_encode(fir_gpu_ctx *ctx, double scale, void *pcm_host);
+/* Same into device memory, asynchronous. */
+FIR_GPU_API int fir_gpu_encode_dev(fir_gpu_ctx *ctx, double scale, void *pcm_dev);
+
+/* ---- measurement & synthetic input --------------------------------------- */
+
+FIR_GPU_API int fir_gpu_last_timing(fir_gpu_ctx *ctx, fir_gpu_timing *t);
+
+/* Counter-based synthetic PCM (same integers as oracle_synth_pcm), written to
+ * device memory: any window of any config without materialising the file. */
+FIR_GPU_API int fir_gpu_synth_pcm_dev(fir_gpu_ctx *ctx, uint64_t seed, int64_t first_frame,
+                                      int64_t frames, int32_t channels, int32_t bits,
+                                      int32_t big_endian, int64_t rate, double gain, void *pcm_dev);
+
+/* Register-resident FP64 throughput probes (TFLOP/s) used as the measured
+ * roofline denominator: kind 0 = DFMA pipe, 1 = DMMA (mma.sync m8n8k4 f64). */
+FIR_GPU_API int fir_gpu_fp64_peak(fir_gpu_ctx *ctx, int kind, double seconds, double *tflops);
+
+/* Tuning knob for experiments: FIR kernel variant (0 = default). */
+FIR_GPU_API int fir_gpu_set_variant(fir_gpu_ctx *ctx, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIR_GPU_H */

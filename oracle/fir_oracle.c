@@ -1,0 +1,504 @@
+/*
+ * fir_oracle.c -- CPU ORACLE for the lowcut hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the checker, not the product.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The shipped
+ * path (audio_fir_filter_b200/csrc, host/) never links or calls anything here.
+ *
+ * PARITY UNPINNED: the reference (diskerror/audio-fir-filter) ships no tests,
+ * fixtures or golden vectors, and the arithmetic it calls lives in the sibling
+ * project diskerror/c_lib (WindowedSinc.h, VectorMath.h, AudioSamples.h), which
+ * is neither vendored nor version-pinned (reference Makefile:17-19,27-31) and is
+ * absent from this machine.  What the reference tree itself fixes is restated
+ * literally (index/edge semantics of FilterCore.h:28-76, the argument
+ * normalisation of ProcessFile.cp:48-50, the thread partition of
+ * ProcessFile.cp:64-69, the peak and auto-normalise rule of ProcessFile.cp:92-101).
+ * What lives in c_lib follows the published algorithm the reference README names
+ * (README.md:50 "Windowed-sinc FIR filter, using Blackman window"; README.md:60-62
+ * S. W. Smith, "The Scientist and Engineer's Guide to DSP", ch. 16), with the
+ * decisions D1..D5 listed in DESIGN.md.
+ *
+ * Precision: tap generation and normalisation in x87 80-bit long double, rounded
+ * once to binary64 (north_star: "normalised in extended precision").  The "hi"
+ * FIR keeps FP64 samples and accumulates in long double, so its result is the
+ * correctly rounded sum to within ~1e-19 relative of sum|h*x|.
+ *
+ * Build: gcc -O3 -fPIC -shared -fopenmp-simd -o liboracle.so fir_oracle.c -lm -lpthread
+ *        (see oracle/Makefile).  x86-64 only (needs 80-bit long double).
+ */
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#if LDBL_MANT_DIG < 64
+#error "oracle needs an 80-bit (or wider) long double"
+#endif
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+static const long double PI_L = 3.141592653589793238462643383279502884L;
+
+/* ------------------------------------------------------ tiny parallel-for -- */
+/* No OpenMP runtime (libgomp is not guaranteed on the toolchain that builds
+ * this); checker loops that are worth threading go through this helper. */
+typedef void (*range_fn)(void *ctx, int64_t lo, int64_t hi);
+struct pf_job { range_fn fn; void *ctx; int64_t lo, hi; };
+static void *pf_tramp(void *p) { struct pf_job *j = (struct pf_job *) p; j->fn(j->ctx, j->lo, j->hi); return NULL; }
+
+static int oracle_threads = 0;
+ORACLE_API void oracle_set_threads(int n) { oracle_threads = n; }
+static int n_workers(void)
+{
+	if (oracle_threads > 0) return oracle_threads;
+	long n = sysconf(_SC_NPROCESSORS_ONLN);
+	return n > 0 ? (int) n : 1;
+}
+ORACLE_API int oracle_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int) n : 1; }
+
+static void parallel_for(int64_t lo, int64_t hi, range_fn fn, void *ctx)
+{
+	int nt = n_workers();
+	if (hi - lo < 4096 || nt <= 1) { fn(ctx, lo, hi); return; }
+	if (nt > 256) nt = 256;
+	pthread_t th[256];
+	struct pf_job jobs[256];
+	const int64_t total = hi - lo, chunk = (total + nt - 1) / nt;
+	int started = 0;
+	for (int i = 0; i < nt; ++i) {
+		int64_t s = lo + (int64_t) i * chunk, e = s + chunk < hi ? s + chunk : hi;
+		if (s >= e) break;
+		jobs[i] = (struct pf_job){fn, ctx, s, e};
+		if (pthread_create(&th[i], NULL, pf_tramp, &jobs[i]) != 0) { fn(ctx, s, e); th[i] = 0; }
+		started = i + 1;
+	}
+	for (int i = 0; i < started; ++i) if (th[i]) pthread_join(th[i], NULL);
+}
+
+/* ------------------------------------------------------------------ taps -- */
+
+/* D4: M = round(4 / bw), forced even (Smith ch.16 eq. 16-3: M ~ 4/BW; the filter
+ * needs a centre tap, FilterCore.h:29 getMo2() = M/2).  BASELINE.json's tap
+ * counts (9 601 at 48 kHz/20 Hz, 192 001 at 96 kHz/2 Hz) confirm M = 4*fs/slope. */
+ORACLE_API int64_t oracle_kernel_order(double bw_norm)
+{
+	if (!(bw_norm > 0.0) || !isfinite(bw_norm)) return -1;
+	long double m = 4.0L / (long double) bw_norm;
+	if (m > 1.0e9L) return -1;
+	int64_t M = (int64_t) llroundl(m);
+	if (M & 1) ++M;
+	if (M < 2) M = 2;
+	return M;
+}
+
+/* WindowedSinc<float64_t>(fc, bw) followed by makeLowCut()
+ * (call sites ProcessFile.cp:48-50; body absent, restated from Smith ch.16):
+ *   low-pass   h[i] = sin(2 pi fc (i-M/2)) / (i-M/2)   (2 pi fc at the centre)
+ *              h[i] *= 0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M)
+ *              h   /= sum(h)                       (unity gain at DC)
+ *   low-cut    h = -h ; h[M/2] += 1                (spectral inversion)
+ * All in long double; taps[0..M] receive the values rounded to binary64.
+ * If taps_ld is non-NULL it receives the unrounded long double taps too. */
+ORACLE_API int oracle_build_lowcut(double fc_norm, double bw_norm, double *taps, int64_t n_taps,
+                                   long double *taps_ld)
+{
+	const int64_t M = oracle_kernel_order(bw_norm);
+	if (M < 0 || n_taps != M + 1) return -1;
+	if (!(fc_norm > 0.0) || !(fc_norm < 0.5)) return -2;
+	const int64_t H = M / 2;
+	long double *h = (long double *) malloc((size_t)(M + 1) * sizeof(long double));
+	if (!h) return -3;
+
+	const long double w = 2.0L * PI_L * (long double) fc_norm;
+	long double sum = 0.0L;
+	for (int64_t i = 0; i <= M; ++i) {
+		const long double m = (long double)(i - H);
+		long double s = (i == H) ? w : sinl(w * m) / m;
+		const long double a = 2.0L * PI_L * (long double) i / (long double) M;
+		const long double win = 0.42L - 0.5L * cosl(a) + 0.08L * cosl(2.0L * a);
+		h[i] = s * win;
+	}
+	/* sum smallest-magnitude-first would be overkill at 64-bit mantissa; a plain
+	 * two-ended sweep keeps symmetric partners together. */
+	for (int64_t i = 0; i < H; ++i) sum += h[i] + h[M - i];
+	sum += h[H];
+
+	for (int64_t i = 0; i <= M; ++i) {
+		long double v = -(h[i] / sum);
+		if (i == H) v += 1.0L;
+		if (taps_ld) taps_ld[i] = v;
+		taps[i] = (double) v;
+	}
+	free(h);
+	return 0;
+}
+
+/* ------------------------------------------------------------------- FIR -- */
+
+/* One output sample of the zero-padded correlation that FilterCore.h:57-76
+ * computes in three loops:
+ *     y[n] = sum_{k=0..M} h[k] * x[n - H + k],   x[j] = 0 outside [0, N).
+ * Prologue  (FilterCore.h:57-61): n <  H      -> last  n+H+1   taps on x[0..)
+ * Main body (FilterCore.h:64-69): H <= n < N-H -> all taps on x[n-H..)
+ * Epilogue  (FilterCore.h:72-76): n >= N-H    -> first N-n+H taps on x[n-H..)
+ * All three are the same clipped sum, written once here. */
+static inline void clip_range(int64_t n, int64_t N, int64_t H, int64_t M, int64_t *k0, int64_t *k1)
+{
+	int64_t lo = H - n;           /* first k with n-H+k >= 0 */
+	int64_t hi = N - 1 - n + H;   /* last  k with n-H+k <= N-1 */
+	*k0 = lo > 0 ? lo : 0;
+	*k1 = hi < M ? hi : M;
+}
+
+/* "hi" mode (decision D1, primary): FP64 samples, long double accumulate, no
+ * float32 narrowing.  Output samples [start, end) of one channel. */
+struct fir_ctx { const double *x; int64_t N; const double *h; int64_t M; double *y; };
+
+static void fir_hi_range(void *p, int64_t start, int64_t end)
+{
+	const struct fir_ctx *c = (const struct fir_ctx *) p;
+	const int64_t H = c->M / 2;
+	for (int64_t n = start; n < end; ++n) {
+		int64_t k0, k1;
+		clip_range(n, c->N, H, c->M, &k0, &k1);
+		/* four independent x87 chains hide the fadd latency; at 64-bit mantissa
+		 * the association order is immaterial (decision D5). */
+		long double a0 = 0.0L, a1 = 0.0L, a2 = 0.0L, a3 = 0.0L;
+		const double *xp = c->x + (n - H);
+		const double *h = c->h;
+		int64_t k = k0;
+		for (; k + 3 <= k1; k += 4) {
+			a0 += (long double) h[k] * (long double) xp[k];
+			a1 += (long double) h[k + 1] * (long double) xp[k + 1];
+			a2 += (long double) h[k + 2] * (long double) xp[k + 2];
+			a3 += (long double) h[k + 3] * (long double) xp[k + 3];
+		}
+		for (; k <= k1; ++k) a0 += (long double) h[k] * (long double) xp[k];
+		c->y[n] = (double) ((a0 + a1) + (a2 + a3));
+	}
+}
+
+ORACLE_API void oracle_fir_hi(const double *x, int64_t N, const double *h, int64_t M, double *y,
+                              int64_t start, int64_t end)
+{
+	struct fir_ctx c = {x, N, h, M, y};
+	parallel_for(start, end, fir_hi_range, &c);
+}
+
+/* The D3 error scale: s[n] = sum_k |h[k] * x[n-H+k]|.  The tolerance the GPU is
+ * held to is |y_gpu - y_hi| <= 1e-12 * s[n]  (a high-pass output is ~0 wherever
+ * the input is ~DC, so "relative to |y|" would be meaningless). */
+static void fir_abs_range(void *p, int64_t start, int64_t end)
+{
+	const struct fir_ctx *c = (const struct fir_ctx *) p;
+	const int64_t H = c->M / 2;
+	for (int64_t n = start; n < end; ++n) {
+		int64_t k0, k1;
+		clip_range(n, c->N, H, c->M, &k0, &k1);
+		double acc = 0.0; /* a scale, not a result: binary64 is plenty */
+		const double *xp = c->x + (n - H);
+		for (int64_t k = k0; k <= k1; ++k) acc += fabs(c->h[k] * xp[k]);
+		c->y[n] = acc;
+	}
+}
+
+ORACLE_API void oracle_fir_abs_scale(const double *x, int64_t N, const double *h, int64_t M,
+                                     double *s, int64_t start, int64_t end)
+{
+	struct fir_ctx c = {x, N, h, M, s};
+	parallel_for(start, end, fir_abs_range, &c);
+}
+
+/* "ref_f32" mode (decision D1, secondary): float32 channel buffers exactly as
+ * the reference stores them (FilterCore.h:21-23), FP64 taps, FP64 accumulate in
+ * ascending tap order, result narrowed with static_cast<float32_t>
+ * (FilterCore.h:59,67,74).  Single range, single thread: the unit the
+ * reference hands each std::thread (ProcessFile.cp:71-78). */
+__attribute__((target_clones("avx512f", "avx2,fma", "default")))
+static void fir_f32_range(const float *x, int64_t N, const double *h, int64_t M, float *y,
+                          int64_t start, int64_t end)
+{
+	const int64_t H = M / 2;
+	for (int64_t n = start; n < end; ++n) {
+		int64_t k0, k1;
+		clip_range(n, N, H, M, &k0, &k1);
+		const float *xp = x + (n - H);
+		double acc = 0.0;
+		/* The c_lib fms() body is unknown; a vectorised reduction is the most
+		 * favourable reading for the CPU baseline, so that is what is timed. */
+#pragma omp simd reduction(+ : acc)
+		for (int64_t k = k0; k <= k1; ++k) acc += h[k] * (double) xp[k];
+		y[n] = (float) acc;
+	}
+}
+
+ORACLE_API void oracle_fir_f32_range(const float *x, int64_t N, const double *h, int64_t M,
+                                     float *y, int64_t start, int64_t end)
+{
+	fir_f32_range(x, N, h, M, y, start, end);
+}
+
+struct f32_job {
+	const float *x;
+	int64_t N;
+	const double *h;
+	int64_t M;
+	float *y;
+	int64_t start, end;
+};
+
+static void *f32_worker(void *p)
+{
+	struct f32_job *j = (struct f32_job *) p;
+	fir_f32_range(j->x, j->N, j->h, j->M, j->y, j->start, j->end);
+	return NULL;
+}
+
+/* The reference's thread fan-out for one channel (ProcessFile.cp:60-83):
+ * chunk = total / num_threads, thread i gets [i*chunk, (i+1)*chunk), the last
+ * thread runs to the end.  `total` here is the number of output samples in
+ * [out_start, out_end) so the same routine can time a bounded slice. */
+ORACLE_API int oracle_fir_f32_threads(const float *x, int64_t N, const double *h, int64_t M,
+                                      float *y, int64_t out_start, int64_t out_end,
+                                      int num_threads)
+{
+	if (num_threads < 1) return -1;
+	pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t) * (size_t) num_threads);
+	struct f32_job *jobs = (struct f32_job *) malloc(sizeof(struct f32_job) * (size_t) num_threads);
+	if (!th || !jobs) { free(th); free(jobs); return -3; }
+	const int64_t total = out_end - out_start;
+	const int64_t chunk = total / num_threads;
+	for (int i = 0; i < num_threads; ++i) {
+		int64_t s = out_start + (int64_t) i * chunk;
+		int64_t e = (i == num_threads - 1) ? out_end : s + chunk;
+		jobs[i] = (struct f32_job){x, N, h, M, y, s, e};
+		pthread_create(&th[i], NULL, f32_worker, &jobs[i]);
+	}
+	for (int i = 0; i < num_threads; ++i) pthread_join(th[i], NULL);
+	free(th);
+	free(jobs);
+	return 0;
+}
+
+/* ------------------------------------------------------------- PCM codec -- */
+
+static inline int64_t load_pcm(const uint8_t *p, int bits, int big_endian)
+{
+	const int nb = bits / 8;
+	uint32_t u = 0;
+	if (big_endian) for (int b = 0; b < nb; ++b) u = (u << 8) | p[b];
+	else            for (int b = nb - 1; b >= 0; --b) u = (u << 8) | p[b];
+	const uint32_t sign = 1u << (bits - 1);
+	/* two's complement sign extension */
+	return (int64_t)(u ^ sign) - (int64_t) sign;
+}
+
+static inline void store_pcm(uint8_t *p, int64_t q, int bits, int big_endian)
+{
+	const int nb = bits / 8;
+	uint32_t u = (uint32_t) q;
+	if (big_endian) for (int b = nb - 1; b >= 0; --b) { p[b] = (uint8_t) u; u >>= 8; }
+	else            for (int b = 0; b < nb; ++b)      { p[b] = (uint8_t) u; u >>= 8; }
+}
+
+/* AudioSamples::readAll (ProcessFile.cp:40-41; body in c_lib): interleaved
+ * signed PCM -> planar samples.  D2: x = int / 2^(bits-1), exact in binary64.
+ * out is planar [channels][stride]. */
+ORACLE_API int oracle_decode_f64(const uint8_t *pcm, int64_t frames, int channels, int bits,
+                                 int big_endian, double *out, int64_t stride)
+{
+	if (bits != 16 && bits != 24 && bits != 32) return -1;
+	const int nb = bits / 8;
+	const double inv = ldexp(1.0, -(bits - 1));
+	for (int64_t f = 0; f < frames; ++f)
+		for (int c = 0; c < channels; ++c)
+			out[(int64_t) c * stride + f] =
+				(double) load_pcm(pcm + ((size_t) f * channels + c) * nb, bits, big_endian) * inv;
+	return 0;
+}
+
+/* Same, into the reference's float32 buffers (32-bit PCM loses 8 bits here,
+ * SURVEY.md section 0.5). */
+ORACLE_API int oracle_decode_f32(const uint8_t *pcm, int64_t frames, int channels, int bits,
+                                 int big_endian, float *out, int64_t stride)
+{
+	if (bits != 16 && bits != 24 && bits != 32) return -1;
+	const int nb = bits / 8;
+	const double inv = ldexp(1.0, -(bits - 1));
+	for (int64_t f = 0; f < frames; ++f)
+		for (int c = 0; c < channels; ++c)
+			out[(int64_t) c * stride + f] = (float)(
+				(double) load_pcm(pcm + ((size_t) f * channels + c) * nb, bits, big_endian) * inv);
+	return 0;
+}
+
+/* VectorMath::max_mag() over every channel (ProcessFile.cp:92-96). */
+ORACLE_API double oracle_peak(const double *y, int64_t frames, int channels, int64_t stride)
+{
+	double m = 0.0;
+	for (int c = 0; c < channels; ++c)
+		for (int64_t f = 0; f < frames; ++f) {
+			double a = fabs(y[(int64_t) c * stride + f]);
+			if (a > m) m = a;
+		}
+	return m;
+}
+
+/* ProcessFile.cp:98: normalise when the peak exceeds full scale or -n is given.
+ * D2: normalise = scale the peak to 1.0.  Returns the gain to encode with. */
+ORACLE_API double oracle_scale_for_peak(double peak, int normalize)
+{
+	if ((peak > 1.0 || normalize) && peak > 0.0) return 1.0 / peak;
+	return 1.0;
+}
+
+/* AudioSamples::normalize + writeAll(buf, true) (ProcessFile.cp:100,117; bodies in
+ * c_lib).  D2: q = clamp(rint(y * scale * 2^(bits-1))), ties to even, clamp to
+ * [-2^(bits-1), 2^(bits-1)-1], no dither; planar -> interleaved, endian as given.
+ * The product is formed in long double so the oracle's rounding decision is
+ * taken on the (nearly) exact value. */
+ORACLE_API int oracle_encode(const double *y, int64_t frames, int channels, int64_t stride,
+                             double scale, int bits, int big_endian, uint8_t *pcm)
+{
+	if (bits != 16 && bits != 24 && bits != 32) return -1;
+	const int nb = bits / 8;
+	const long double fs = ldexpl(1.0L, bits - 1);
+	const long double lo = -fs, hi = fs - 1.0L;
+	for (int64_t f = 0; f < frames; ++f)
+		for (int c = 0; c < channels; ++c) {
+			long double v = (long double) y[(int64_t) c * stride + f] * (long double) scale * fs;
+			v = rintl(v); /* default rounding mode: to nearest, ties to even */
+			if (v < lo) v = lo;
+			if (v > hi) v = hi;
+			store_pcm(pcm + ((size_t) f * channels + c) * nb, (int64_t) v, bits, big_endian);
+		}
+	return 0;
+}
+
+/* float32-faithful encode for the ref_f32 mode: the scaled value is a float32
+ * (the reference's AudioBuffer holds float32, FilterCore.h:23). */
+ORACLE_API int oracle_encode_f32(const float *y, int64_t frames, int channels, int64_t stride,
+                                 float scale, int bits, int big_endian, uint8_t *pcm)
+{
+	if (bits != 16 && bits != 24 && bits != 32) return -1;
+	const int nb = bits / 8;
+	const double fs = ldexp(1.0, bits - 1);
+	for (int64_t f = 0; f < frames; ++f)
+		for (int c = 0; c < channels; ++c) {
+			float s = y[(int64_t) c * stride + f] * scale; /* normalize() in place, float32 */
+			double v = rint((double) s * fs);
+			if (v < -fs) v = -fs;
+			if (v > fs - 1.0) v = fs - 1.0;
+			store_pcm(pcm + ((size_t) f * channels + c) * nb, (int64_t) v, bits, big_endian);
+		}
+	return 0;
+}
+
+/* ------------------------------------------------- synthetic PCM -- */
+
+/* Counter-based generator so any window of any config is reproducible on host
+ * and device without materialising the file.  SplitMix64 of (seed, channel,
+ * frame) for the noise term; the deterministic terms are a DC offset, a 5 Hz
+ * rumble and a 1 kHz tone.  Everything is evaluated in binary64 with sinpi-free,
+ * table-free arithmetic that the CUDA generator repeats operation for operation,
+ * then QUANTISED to the integer PCM grid -- parity is defined on those integers. */
+static inline uint64_t splitmix64(uint64_t z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+/* triangle-wave "tones": exact in integer arithmetic, so host and device agree
+ * bit for bit with no libm in the loop.  period in frames. */
+static inline double tri(int64_t n, int64_t period)
+{
+	int64_t p = n % period;
+	int64_t half = period / 2;
+	int64_t v = p < half ? p : period - p;          /* 0..half */
+	return (double)(4 * v - 2 * half) / (double)(2 * half); /* -1..1 */
+}
+
+ORACLE_API int64_t oracle_synth_sample(uint64_t seed, int channel, int64_t frame, int bits,
+                                       int64_t rate, double gain)
+{
+	const double fs = ldexp(1.0, bits - 1);
+	uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t) channel << 48) ^ (uint64_t) frame));
+	double noise = ((double)(r >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0; /* [-1,1) */
+	int64_t p_rumble = rate / 5;  if (p_rumble < 2) p_rumble = 2;
+	int64_t p_tone = rate / 1000; if (p_tone < 2) p_tone = 2;
+	double v = 0.05 + 0.2 * tri(frame + 17 * channel, p_rumble)
+	         + 0.3 * tri(frame + 5 * channel, p_tone) + 0.1 * noise;
+	v *= gain;
+	double q = rint(v * fs);
+	if (q < -fs) q = -fs;
+	if (q > fs - 1.0) q = fs - 1.0;
+	return (int64_t) q;
+}
+
+struct synth_ctx { uint64_t seed; int64_t first; int channels, bits, be; int64_t rate; double gain; uint8_t *pcm; };
+static void synth_range(void *p, int64_t lo, int64_t hi)
+{
+	const struct synth_ctx *s = (const struct synth_ctx *) p;
+	const int nb = s->bits / 8;
+	for (int64_t f = lo; f < hi; ++f)
+		for (int c = 0; c < s->channels; ++c)
+			store_pcm(s->pcm + ((size_t) f * s->channels + c) * nb,
+			          oracle_synth_sample(s->seed, c, s->first + f, s->bits, s->rate, s->gain),
+			          s->bits, s->be);
+}
+
+ORACLE_API int oracle_synth_pcm(uint64_t seed, int64_t first_frame, int64_t frames, int channels,
+                                int bits, int big_endian, int64_t rate, double gain, uint8_t *pcm)
+{
+	if (bits != 16 && bits != 24 && bits != 32) return -1;
+	struct synth_ctx c = {seed, first_frame, channels, bits, big_endian, rate, gain, pcm};
+	parallel_for(0, frames, synth_range, &c);
+	return 0;
+}
+
+/* ------------------------------------------------------- whole-path oracle -- */
+
+/* process_file's arithmetic (ProcessFile.cp:41-101,117) end to end in "hi" mode:
+ * decode -> build taps -> FIR every channel -> peak -> scale rule -> encode.
+ * pcm_in may carry `halo_l`/`halo_r` real frames either side of the `frames`
+ * that are to be produced (sample-block sharding); zeros are
+ * implied beyond them.  y_out (optional) receives planar FP64 [channels][frames].
+ * If scale_in > 0 it is used instead of the locally derived one (the multi-GPU
+ * path all-reduces the peak first). */
+ORACLE_API int oracle_process(const uint8_t *pcm_in, int64_t frames, int channels, int bits,
+                              int big_endian, int64_t halo_l, int64_t halo_r, double fc_norm,
+                              double bw_norm, int normalize, double scale_in, uint8_t *pcm_out,
+                              double *y_out, double *peak_out, double *scale_out)
+{
+	const int64_t M = oracle_kernel_order(bw_norm);
+	if (M < 0) return -1;
+	const int64_t tot = halo_l + frames + halo_r;
+	double *taps = (double *) malloc(sizeof(double) * (size_t)(M + 1));
+	double *x = (double *) malloc(sizeof(double) * (size_t) tot * channels);
+	double *y = (double *) calloc((size_t) tot * channels, sizeof(double));
+	if (!taps || !x || !y) { free(taps); free(x); free(y); return -3; }
+	int rc = oracle_build_lowcut(fc_norm, bw_norm, taps, M + 1, NULL);
+	if (!rc) rc = oracle_decode_f64(pcm_in, tot, channels, bits, big_endian, x, tot);
+	if (!rc) {
+		for (int c = 0; c < channels; ++c)
+			oracle_fir_hi(x + (int64_t) c * tot, tot, taps, M, y + (int64_t) c * tot, halo_l,
+			              halo_l + frames);
+		double peak = oracle_peak(y + halo_l, frames, channels, tot);
+		double scale = scale_in > 0.0 ? scale_in : oracle_scale_for_peak(peak, normalize);
+		if (peak_out) *peak_out = peak;
+		if (scale_out) *scale_out = scale;
+		if (y_out)
+			for (int c = 0; c < channels; ++c)
+				memcpy(y_out + (int64_t) c * frames, y + (int64_t) c * tot + halo_l,
+				       sizeof(double) * (size_t) frames);
+		if (pcm_out)
+			rc = oracle_encode(y + halo_l, frames, channels, tot, scale, bits, big_endian, pcm_out);
+	}
+	free(taps); free(x); free(y);
+	return rc;
+}
