@@ -420,6 +420,28 @@ int fir_gpu_set_variant(fir_gpu_ctx* c, int variant)
 	return FIR_GPU_OK;
 }
 
+int fir_gpu_variant_count(void)
+{
+	int nv = 0;
+	fir_variants(&nv);
+	return nv;
+}
+
+const char* fir_gpu_variant_name(int variant)
+{
+	int nv = 0;
+	const FirVariant* vs = fir_variants(&nv);
+	return (variant >= 0 && variant < nv) ? vs[variant].name : "";
+}
+
+int fir_gpu_set_x_budget(fir_gpu_ctx* c, int64_t bytes)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	if (bytes < (1 << 20)) return fail(FIR_GPU_ERR_INVALID, "input scratch budget must be at least 1 MiB");
+	c->x_budget_bytes = bytes;
+	return FIR_GPU_OK;
+}
+
 // ------------------------------------------------------------ build_kernel
 
 static int alloc_kernel(fir_gpu_ctx* c, int64_t n_taps, fir_gpu_kernel** out)

@@ -3,6 +3,7 @@
 // WindowedSinc<float64_t>(fc, bw) + makeLowCut() (ProcessFile.cp:48-50; recipe per
 // the reference README.md:50,60-62 -> Smith, DSP Guide ch.16):
 //     lp[i] = sin(2 pi fc (i-H)) / (i-H) * (0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M))
+//             (the window is evaluated in its cancellation-free form, see lowpass_tap)
 //     h[i]  = -lp[i] / sum(lp),  h[H] += 1
 // "Normalised in extended precision": the sum runs in double-double (~106 bit),
 // the angles are reduced exactly (products and quotients keep their FMA
@@ -58,6 +59,7 @@ __device__ __forceinline__ double cospi_dd(double p_hi, double p_lo)
 __device__ __forceinline__ double lowpass_tap(long long i, long long M, double fc)
 {
 	const long long H = M / 2;
+	if (i > H) i = M - i; // evaluate the left half only: h[i] == h[M-i] bit for bit
 	const double m = (double) (i - H);
 	double s;
 	if (i == H) {
@@ -69,12 +71,16 @@ __device__ __forceinline__ double lowpass_tap(long long i, long long M, double f
 		const double p_lo = fma(two_fc, m, -p_hi);      // exact remainder
 		s = __ddiv_rn(sinpi_dd(p_hi, p_lo), m);
 	}
-	const double two_i = (double) (2 * i), dM = (double) M;
-	const double t_hi = __ddiv_rn(two_i, dM);           // 2 i / M half-turns
-	const double t_lo = __ddiv_rn(fma(-t_hi, dM, two_i), dM);
-	const double c1 = cospi_dd(t_hi, t_lo);
-	const double c2 = cospi_dd(2.0 * t_hi, 2.0 * t_lo);
-	const double win = __dadd_rn(__dsub_rn(0.42, __dmul_rn(0.5, c1)), __dmul_rn(0.08, c2));
+	// Blackman window without cancellation: with u = sin(pi i / M),
+	//   0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M) = u^2 (0.36 + 0.64 u^2)
+	// (0.42 - 0.5 + 0.08 = 0), so the small taps at the ends keep full relative
+	// accuracy instead of the ~1e-17 absolute error of the three-term form.
+	const double di = (double) i, dM = (double) M;
+	const double t_hi = __ddiv_rn(di, dM);              // i / M half-turns
+	const double t_lo = __ddiv_rn(fma(-t_hi, dM, di), dM);
+	const double u = sinpi_dd(t_hi, t_lo);
+	const double u2 = __dmul_rn(u, u);
+	const double win = __dmul_rn(u2, fma(0.64, u2, 0.36));
 	return __dmul_rn(s, win);
 }
 

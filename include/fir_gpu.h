@@ -175,8 +175,13 @@ FIR_GPU_API int fir_gpu_synth_pcm_dev(fir_gpu_ctx *ctx, uint64_t seed, int64_t f
  * roofline denominator: kind 0 = DFMA pipe, 1 = DMMA (mma.sync m8n8k4 f64). */
 FIR_GPU_API int fir_gpu_fp64_peak(fir_gpu_ctx *ctx, int kind, double seconds, double *tflops);
 
-/* Tuning knob for experiments: FIR kernel variant (0 = default). */
+/* Tuning knobs for experiments: FIR kernel variant (0 = default), and the bound
+ * on the decoded FP64 input scratch (files longer than this stream through it
+ * chunk by chunk; the result does not depend on it). */
 FIR_GPU_API int fir_gpu_set_variant(fir_gpu_ctx *ctx, int variant);
+FIR_GPU_API int fir_gpu_variant_count(void);
+FIR_GPU_API const char *fir_gpu_variant_name(int variant);
+FIR_GPU_API int fir_gpu_set_x_budget(fir_gpu_ctx *ctx, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -114,12 +114,16 @@ ORACLE_API int oracle_build_lowcut(double fc_norm, double bw_norm, double *taps,
 
 	const long double w = 2.0L * PI_L * (long double) fc_norm;
 	long double sum = 0.0L;
-	for (int64_t i = 0; i <= M; ++i) {
+	/* The filter is symmetric (h[i] == h[M-i]); FilterCore.h:57-76 relies on that
+	 * when it correlates instead of convolving.  Evaluate the left half and the
+	 * centre, mirror the rest, so the symmetry holds bit for bit. */
+	for (int64_t i = 0; i <= H; ++i) {
 		const long double m = (long double)(i - H);
 		long double s = (i == H) ? w : sinl(w * m) / m;
 		const long double a = 2.0L * PI_L * (long double) i / (long double) M;
 		const long double win = 0.42L - 0.5L * cosl(a) + 0.08L * cosl(2.0L * a);
 		h[i] = s * win;
+		h[M - i] = h[i];
 	}
 	/* sum smallest-magnitude-first would be overkill at 64-bit mantissa; a plain
 	 * two-ended sweep keeps symmetric partners together. */

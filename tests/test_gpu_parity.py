@@ -1,0 +1,390 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the oracle.
+
+Bars (BASELINE.json north_star; decisions D1-D5 in DESIGN.md):
+  * FP64 filtered signal: |y_gpu - y_oracle| <= 1e-12 * sum_k |h_k x_{n-H+k}|      (D3)
+  * taps: within 1 ulp of the oracle's long-double taps
+  * decode: exact;  encode / whole path: PCM bit-exact except a COUNTED number of
+    +-1-LSB flips at rounding boundaries (asserted to be a tiny fraction)
+  * tiling / chunking / variant / sharding invariance: bit-exact
+"""
+import numpy as np
+import pytest
+
+from conftest import CONFIGS, golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+TAP_ULPS = 4.0   # binary64 sinpi/div/mul chain per tap + double-double normalisation
+
+
+def pcm_to_int(pcm, bits, be):
+    nb = bits // 8
+    b = pcm.reshape(-1, nb).astype(np.int64)
+    if be:
+        b = b[:, ::-1]
+    v = np.zeros(b.shape[0], dtype=np.int64)
+    for k in range(nb):
+        v |= b[:, k] << (8 * k)
+    sign = 1 << (bits - 1)
+    return (v ^ sign) - sign
+
+
+def lsb_flips(a, b, bits, be):
+    """(#samples that differ, max |difference| in LSB)."""
+    d = np.abs(pcm_to_int(a, bits, be) - pcm_to_int(b, bits, be))
+    return int(np.count_nonzero(d)), int(d.max(initial=0))
+
+
+# ------------------------------------------------------------------ taps ----------
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 5])
+def test_build_kernel_matches_oracle_taps(ctx, oracle_mod, cfg):
+    c = CONFIGS[cfg]
+    fc, bw = c["freq"] / c["fs"], c["slope"] / c["fs"]
+    k = ctx.build_kernel(fc, bw)
+    assert k.num_taps == c["taps"] and k.half_len == (c["taps"] - 1) // 2
+    got = k.taps()
+    want, ld = oracle_mod.build_lowcut(fc, bw, want_ld=True)
+    err = np.abs(got.astype(np.longdouble) - ld).astype(np.float64)
+    ulps = err / (np.spacing(np.abs(want)) + 1e-19)
+    print(f"config {cfg}: max tap error {ulps.max():.2f} ulp, {np.count_nonzero(got != want)} of {got.size} differ")
+    assert np.all(ulps <= TAP_ULPS), float(ulps.max())
+    assert np.array_equal(got, got[::-1])                       # symmetric bit for bit
+    assert abs(float(got.astype(np.longdouble).sum())) < 1e-15   # DC removed
+    k.free()
+
+
+@pytest.mark.parametrize("name", ["small", "odd"])
+def test_build_kernel_matches_mpmath_golden(ctx, name):
+    g = golden(f"taps_{name}.npz")
+    k = ctx.build_kernel(float(g["fc"]), float(g["bw"]))
+    got = k.taps()
+    assert got.shape == g["taps"].shape
+    assert np.all(np.abs(got - g["taps"]) <= TAP_ULPS * (np.spacing(np.abs(g["taps"])) + 1e-19))
+    k.free()
+
+
+def test_build_kernel_rejects_bad_arguments(ctx):
+    from audio_fir_filter_b200 import capi
+
+    for fc, bw in [(0.01, 0.0), (0.01, -1.0), (0.0, 0.01), (0.5, 0.01), (0.01, 1e-12)]:
+        with pytest.raises(capi.FirGpuError) as e:
+            ctx.build_kernel(fc, bw)
+        assert e.value.code == capi.ERR_INVALID
+
+
+# ------------------------------------------------------------------- FIR ----------
+
+def check_fir(ctx, oracle_mod, taps, x):
+    k = ctx.kernel_from_taps(taps)
+    y = ctx.filter_f64(k, x)
+    k.free()
+    x2 = np.atleast_2d(x)
+    worst = 0.0
+    for c in range(x2.shape[0]):
+        want = oracle_mod.fir_hi(x2[c], taps)
+        scale = oracle_mod.fir_abs_scale(x2[c], taps)
+        err = np.abs(y[c] - want)
+        assert np.all(err <= TOL * scale + 1e-300), float((err / np.maximum(scale, 1e-300)).max())
+        worst = max(worst, float((err / np.maximum(scale, 1e-300)).max()))
+    return y, worst
+
+
+@pytest.mark.parametrize("N", [1, 2, 15, 16, 17, 480, 961, 962, 4095, 4096, 4097, 10000, 70001])
+def test_fir_f64_any_length_including_shorter_than_the_kernel(ctx, oracle_mod, N):
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000)      # 961 taps
+    x = np.random.default_rng(N).uniform(-1, 1, N)
+    check_fir(ctx, oracle_mod, taps, x)
+
+
+def test_fir_f64_multichannel_long_kernel(ctx, oracle_mod):
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 20.0 / 48000)       # config 1 kernel, 9601 taps
+    x = np.random.default_rng(3).uniform(-1, 1, (3, 40000))
+    _, worst = check_fir(ctx, oracle_mod, taps, x)
+    assert worst < 1e-13
+
+
+def test_fir_f64_against_reference_filtercore_golden(ctx, oracle_mod):
+    for name in ("body", "maketest", "short"):
+        g = golden(f"filtercore_{name}.npz")
+        k = ctx.kernel_from_taps(g["taps"])
+        y = ctx.filter_f64(k, g["x"].astype(np.float64))[0]
+        k.free()
+        ulp = np.spacing(np.abs(g["y_full"])).astype(np.float64)
+        # the reference narrows to float32 on store (FilterCore.h:59,67,74)
+        assert np.all(np.abs(y - g["y_full"]) <= 0.5 * ulp + 1e-12)
+        flips = np.count_nonzero(y.astype(np.float32) != g["y_full"])
+        assert flips <= 0.002 * y.size, flips
+
+
+def test_fir_impulse_returns_the_taps_exactly(ctx, oracle_mod):
+    taps = oracle_mod.build_lowcut(30.0 / 44100, 100.0 / 44100)
+    M = taps.size - 1
+    H = M // 2
+    N = 3 * M
+    x = np.zeros(N)
+    p = N // 2 + 3
+    x[p] = 1.0
+    k = ctx.kernel_from_taps(taps)
+    y = ctx.filter_f64(k, x)[0]
+    assert np.array_equal(y[p - H:p + H + 1], taps[::-1])
+    assert not y[:p - H].any() and not y[p + H + 1:].any()
+    # constant -> 0 in the steady state, gain ~ 1 at Nyquist
+    y = ctx.filter_f64(k, np.full(N, 0.5))[0]
+    assert np.max(np.abs(y[H:N - H])) < 1e-15
+    y = ctx.filter_f64(k, (-1.0) ** np.arange(N))[0]
+    assert np.max(np.abs(np.abs(y[H:N - H]) - 1.0)) < 1e-3
+    k.free()
+
+
+def test_fir_is_invariant_to_variant_and_chunking(ctx, oracle_mod):
+    """One ascending FMA chain per output: the bits do not depend on the CTA shape,
+    the tap-tile size, the pipeline depth or how the file is chunked."""
+    from audio_fir_filter_b200 import capi
+
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 60.0 / 48000)       # 3201 taps
+    x = np.random.default_rng(11).uniform(-1, 1, (2, 50000))
+    k = ctx.kernel_from_taps(taps)
+    base = None
+    try:
+        for v, name in enumerate(capi.variant_names()):
+            ctx.set_variant(v)
+            y = ctx.filter_f64(k, x)
+            if base is None:
+                base = y
+            assert np.array_equal(y, base), name
+    finally:
+        ctx.set_variant(0)
+        k.free()
+
+
+# ------------------------------------------------------------------- PCM ----------
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+@pytest.mark.parametrize("be", [False, True])
+@pytest.mark.parametrize("channels", [1, 2, 3, 8, 16])
+def test_pcm_path_all_formats(ctx, oracle_mod, bits, be, channels):
+    fs, freq, slope = 8000, 40.0, 50.0                                # 641 taps
+    frames = 5000 + 7 * channels
+    pcm = oracle_mod.synth_pcm(bits * 100 + channels, 0, frames, channels, bits, be, fs)
+    k = ctx.build_kernel(freq / fs, slope / fs)
+    ctx.apply(k, pcm, frames, channels, bits, be)
+    # decode + FIR: the parked FP64 signal against the oracle on the oracle's decode
+    y = ctx.parked(frames, channels)
+    taps = k.taps()
+    x = oracle_mod.decode(pcm, frames, channels, bits, be)
+    for c in range(channels):
+        want = oracle_mod.fir_hi(x[c], taps)
+        scale = oracle_mod.fir_abs_scale(x[c], taps)
+        assert np.all(np.abs(y[c] - want) <= TOL * scale + 1e-300)
+    # peak: fused epilogue value == stand-alone kernel == max|y| of what is parked
+    pk = ctx.peak()
+    assert pk == float(np.abs(y).max())
+    assert ctx.peak_recompute() == pk
+    # encode: bit-exact against the oracle's encode of the SAME parked signal
+    for scale_ in (1.0, 1.0 / pk, 3.0):                               # 3.0 clips
+        out = np.empty_like(pcm)
+        ctx.encode(scale_, out)
+        want = oracle_mod.encode(y, scale_, bits, be)
+        n, mx = lsb_flips(out, want, bits, be)
+        assert mx <= 1 and n <= max(2, 1e-4 * out.size), (n, mx)
+    k.free()
+
+
+def test_decode_is_exact_identity_kernel(ctx, oracle_mod):
+    """A 1-tap kernel h = [1] turns apply+encode into decode -> encode: bytes in == bytes out."""
+    for bits, be, ch in [(16, True, 2), (24, False, 5), (32, False, 16), (24, True, 1)]:
+        frames = 33333
+        pcm = np.random.default_rng(bits + ch).integers(0, 256, frames * ch * bits // 8, dtype=np.uint8)
+        k = ctx.kernel_from_taps(np.array([1.0]))
+        ctx.apply(k, pcm, frames, ch, bits, be)
+        y = ctx.parked(frames, ch)
+        assert np.array_equal(y, oracle_mod.decode(pcm, frames, ch, bits, be))
+        out = np.zeros_like(pcm)
+        ctx.encode(1.0, out)
+        assert np.array_equal(out, pcm)
+        k.free()
+
+
+@pytest.mark.parametrize("cfg,frames", [(1, 300_000), (2, 400_000)])
+def test_whole_path_reduced_configs(ctx, oracle_mod, cfg, frames):
+    """Configs 1 and 2 (real kernels, real formats, -n on config 2) on a shortened file,
+    whole path against oracle_process: y within 1e-12, PCM bit-exact modulo counted flips."""
+    from audio_fir_filter_b200 import FilterOptions, PcmInfo, process_pcm
+
+    c = CONFIGS[cfg]
+    pcm = oracle_mod.synth_pcm(0xF1F1F1, 0, frames, c["channels"], c["bits"], c["be"], c["fs"])
+    info = PcmInfo(frames, c["channels"], c["bits"], c["be"], float(c["fs"]))
+    opts = FilterOptions(freq=c["freq"], slope=c["slope"], normalize=c["normalize"])
+    out = np.empty_like(pcm)
+    r = process_pcm(ctx, pcm, info, opts, out)
+    assert r["taps"] == c["taps"]
+    want = oracle_mod.process(pcm, frames, c["channels"], c["bits"], c["be"], c["freq"] / c["fs"],
+                              c["slope"] / c["fs"], c["normalize"])
+    y = ctx.parked(frames, c["channels"])
+    assert np.max(np.abs(y - want["y"])) <= 1e-12 * np.abs(want["y"]).max()
+    assert abs(r["peak"] - want["peak"]) <= 1e-12 * want["peak"]
+    assert abs(r["scale"] - want["scale"]) <= 1e-12 * want["scale"]
+    n, mx = lsb_flips(out, want["pcm"], c["bits"], c["be"])
+    print(f"config {cfg}: {n} of {out.size // (c['bits'] // 8)} samples differ by 1 LSB")
+    assert mx <= 1 and n <= 1e-5 * out.size + 2, (n, mx)
+    if c["normalize"]:
+        v = pcm_to_int(out, c["bits"], c["be"])
+        assert max(v.max(), -v.min()) >= (1 << (c["bits"] - 1)) - 1
+
+
+def test_auto_normalise_fires_only_above_full_scale(ctx, oracle_mod):
+    from audio_fir_filter_b200 import FilterOptions, PcmInfo, process_pcm
+
+    fs, frames, ch, bits = 8000, 20000, 2, 24
+    opts = FilterOptions(freq=40.0, slope=50.0)
+    info = PcmInfo(frames, ch, bits, False, float(fs))
+    quiet = oracle_mod.synth_pcm(5, 0, frames, ch, bits, False, fs, gain=1.0)
+    out = np.empty_like(quiet)
+    r = process_pcm(ctx, quiet, info, opts, out)
+    assert r["peak"] <= 1.0 and r["scale"] == 1.0
+    # a full-scale square wave overshoots after the high-pass (Gibbs): peak > 1 -> scaled down
+    sq = np.where((np.arange(frames) // 50) % 2 == 0, (1 << 23) - 1, -(1 << 23)).astype(np.int32)
+    b = np.stack([(sq >> s) & 0xFF for s in (0, 8, 16)], axis=1).astype(np.uint8)
+    loud = np.repeat(b[:, None, :], ch, axis=1).reshape(-1)
+    r = process_pcm(ctx, loud, info, opts, out)
+    assert r["peak"] > 1.0 and r["scale"] == 1.0 / r["peak"]
+    want = oracle_mod.process(loud, frames, ch, bits, False, 40.0 / fs, 50.0 / fs, False)
+    n, mx = lsb_flips(out, want["pcm"], bits, False)
+    assert mx <= 1 and n <= 4
+
+
+# ------------------------------------------------------- sharding / chunking ------
+
+def test_sample_block_sharding_is_bit_exact(ctx, oracle_mod):
+    """One long file as 1, 2, 3 and 8 sample blocks with (taps-1) halo (several contexts
+    on this one GPU standing in for the ranks): same peak, same PCM, bit for bit."""
+    from audio_fir_filter_b200 import Context, FilterOptions, PcmInfo, process_pcm, process_pcm_sharded
+
+    c = CONFIGS[5]
+    fs, frames, ch, bits = 8000, 60_003, 4, 32
+    pcm = oracle_mod.synth_pcm(9, 0, frames, ch, bits, False, fs)
+    info = PcmInfo(frames, ch, bits, False, float(fs))
+    opts = FilterOptions(freq=c["freq"] * fs / c["fs"], slope=c["slope"] * fs / c["fs"] * 40, normalize=True)
+    whole = np.empty_like(pcm)
+    r0 = process_pcm(ctx, pcm, info, opts, whole)
+    y0 = ctx.parked(frames, ch)
+    for world in (2, 3, 8):
+        ctxs = [Context(0) for _ in range(world)]
+        out, r = process_pcm_sharded(ctxs, pcm, info, opts)
+        assert r["peak"] == r0["peak"] and r["scale"] == r0["scale"]
+        assert np.array_equal(out, whole)
+        for b in r["blocks"]:
+            if b.frames:
+                assert np.array_equal(ctxs[b.rank].parked(b.frames, ch), y0[:, b.start:b.start + b.frames])
+        for cx in ctxs:
+            cx.close()
+
+
+def test_chunked_streaming_is_bit_exact(ctx, oracle_mod):
+    """Files larger than the decoded-input scratch stream through it chunk by chunk."""
+    fs, frames, ch, bits = 8000, 300_000, 2, 16
+    pcm = oracle_mod.synth_pcm(21, 0, frames, ch, bits, True, fs)
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)
+    ctx.apply(k, pcm, frames, ch, bits, True)
+    y0 = ctx.parked(frames, ch)
+    p0 = ctx.peak()
+    try:
+        ctx.set_x_budget(1 << 20)          # 1 MiB -> ~16 chunks
+        ctx.apply(k, pcm, frames, ch, bits, True)
+        assert ctx.last_timing()["fir_launches"] > 4
+        assert np.array_equal(ctx.parked(frames, ch), y0) and ctx.peak() == p0
+    finally:
+        ctx.set_x_budget(2 << 30)
+        k.free()
+
+
+# ------------------------------------------------------- synthetic generator ------
+
+@pytest.mark.parametrize("bits,be,ch", [(16, True, 2), (24, False, 2), (24, False, 8), (32, False, 16)])
+def test_device_synth_equals_oracle_synth(ctx, oracle_mod, bits, be, ch):
+    import torch
+
+    frames, first, rate = 20000, 123_456_789, 96000
+    d = torch.empty(frames * ch * bits // 8, dtype=torch.uint8, device="cuda:0")
+    ctx.synth_pcm_dev(0xF1F1F1, first, frames, ch, bits, be, rate, 1.0, d)
+    ctx.synchronize()
+    want = oracle_mod.synth_pcm(0xF1F1F1, first, frames, ch, bits, be, rate)
+    assert np.array_equal(d.cpu().numpy(), want)
+
+
+# ------------------------------------------------- full BASELINE sizes: properties --
+
+def test_config1_full_size_windows_and_properties(ctx, oracle_mod):
+    """Config 1 at its full size (60 s stereo 48 kHz 24-bit, 9601 taps), device-resident
+    synthetic PCM: sampled windows (both file edges + random interior) against the oracle,
+    plus DC rejection over the whole file."""
+    import torch
+
+    c = CONFIGS[1]
+    frames, ch, bits, fs = c["frames"], c["channels"], c["bits"], c["fs"]
+    fb = ch * bits // 8
+    d_in = torch.empty(frames * fb, dtype=torch.uint8, device="cuda:0")
+    ctx.synth_pcm_dev(0xF1F1F1, 0, frames, ch, bits, False, fs, 1.0, d_in)
+    k = ctx.build_kernel(c["freq"] / fs, c["slope"] / fs)
+    ctx.apply_dev(k, d_in, frames, ch, bits, False)
+    pk = ctx.peak()
+    y = ctx.parked(frames, ch)
+    assert pk == float(np.abs(y).max()) and pk < 1.0
+    taps = k.taps()
+    H = k.half_len
+    W = 4096
+    rng = np.random.default_rng(1)
+    starts = [0, frames - W] + [int(s) for s in rng.integers(H, frames - H - W, 6)]
+    for s in starts:
+        lo, hi = max(0, s - H), min(frames, s + W + H)
+        seg = oracle_mod.synth_pcm(0xF1F1F1, lo, hi - lo, ch, bits, False, fs)
+        x = oracle_mod.decode(seg, hi - lo, ch, bits, False)
+        for cc in range(ch):
+            xx = x[cc]
+            # [lo, hi) is clipped only at the true file ends, where zero padding is right
+            want = oracle_mod.fir_hi(xx, taps, s - lo, s - lo + W)[s - lo:s - lo + W]
+            scale = oracle_mod.fir_abs_scale(xx, taps, s - lo, s - lo + W)[s - lo:s - lo + W]
+            got = y[cc, s:s + W]
+            assert np.all(np.abs(got - want) <= TOL * scale)
+    # the 0.05 FS offset is gone in the steady state
+    assert abs(y[:, H:frames - H].mean()) < 1e-6
+    out = torch.empty_like(d_in)
+    ctx.encode_dev(1.0, out)
+    ctx.synchronize()
+    want_pcm = oracle_mod.encode(y[:, :65536], 1.0, bits, False)
+    n, mx = lsb_flips(out[:65536 * fb].cpu().numpy(), want_pcm, bits, False)
+    assert mx <= 1 and n <= 2
+    k.free()
+
+
+# ------------------------------------------------------------- error paths --------
+
+def test_error_behaviour(ctx):
+    from audio_fir_filter_b200 import capi
+
+    k = ctx.kernel_from_taps(np.array([0.25, 0.5, 0.25]))
+    pcm = np.zeros(64, dtype=np.uint8)
+    for kw in (dict(bits=12), dict(channels=0), dict(frames=-1)):
+        a = dict(frames=8, channels=2, bits=16)
+        a.update(kw)
+        with pytest.raises(capi.FirGpuError) as e:
+            ctx.apply(k, pcm, a["frames"], a["channels"], a["bits"], False)
+        assert e.value.code == capi.ERR_INVALID
+    with pytest.raises(capi.FirGpuError) as e:
+        ctx.kernel_from_taps(np.array([0.5, 0.5]))      # even tap count: no centre tap
+    assert e.value.code == capi.ERR_INVALID
+    c2 = capi.Context(0)
+    with pytest.raises(capi.FirGpuError) as e:
+        c2.peak()                                        # nothing parked yet
+    assert e.value.code == capi.ERR_STATE
+    with pytest.raises(capi.FirGpuError) as e:
+        c2.encode(1.0, pcm)
+    assert e.value.code == capi.ERR_STATE
+    c2.close()
+    # empty payload: legal, produces nothing
+    ctx.apply(k, pcm, 0, 2, 16, False)
+    assert ctx.peak() == 0.0
+    ctx.encode(1.0, pcm)
+    k.free()

@@ -1,0 +1,239 @@
+"""CPU tests: the oracle against the committed golden fixtures and against the
+known-answer properties SURVEY.md section 8c lists (the reference ships no tests of
+its own, so these are the pins)."""
+import numpy as np
+import pytest
+
+from conftest import CONFIGS, golden
+
+
+# ---------------------------------------------------------------- taps ------------
+
+@pytest.mark.parametrize("name", ["small", "cfg1", "odd"])
+def test_taps_match_mpmath_golden(oracle_mod, name):
+    g = golden(f"taps_{name}.npz")
+    taps = oracle_mod.build_lowcut(float(g["fc"]), float(g["bw"]))
+    ref = g["taps"]
+    assert taps.shape == ref.shape
+    # 80-bit evaluation, one rounding: at most 1 ulp from the 50-digit value (a
+    # near-tie may round the other way), plus an absolute floor where the window is 0.
+    tol = np.spacing(np.abs(ref)) + 1e-19
+    assert np.all(np.abs(taps - ref) <= tol)
+    assert np.count_nonzero(taps != ref) <= 0.05 * ref.size
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_tap_counts_of_the_five_configs(oracle_mod, cfg):
+    c = CONFIGS[cfg]
+    assert oracle_mod.kernel_order(c["slope"] / c["fs"]) + 1 == c["taps"]
+
+
+def test_order_is_forced_even(oracle_mod):
+    # 4*44100/80 = 2205 -> 2206 (FilterCore.h:29 needs a centre tap M/2)
+    assert oracle_mod.kernel_order(80.0 / 44100.0) == 2206
+    assert oracle_mod.kernel_order(0.0) == -1
+    assert oracle_mod.kernel_order(-1.0) == -1
+
+
+def test_taps_symmetry_dc_and_nyquist(oracle_mod):
+    taps, ld = oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000, want_ld=True)
+    M = taps.size - 1
+    assert np.array_equal(taps, taps[::-1])             # h[k] == h[M-k] bit for bit
+    assert abs(float(ld.sum())) < 1e-17                  # sum h = 0: DC removed
+    alt = (-1.0) ** np.arange(M + 1)
+    assert abs(abs(float((taps * alt).sum())) - 1.0) < 1e-3   # gain ~ 1 at Nyquist
+    assert taps[M // 2] > 0.99                            # 1 - (2 fc)/sum ...
+
+
+def test_bad_cutoff_rejected(oracle_mod):
+    with pytest.raises(ValueError):
+        oracle_mod.build_lowcut(0.6, 0.01)
+    with pytest.raises(ValueError):
+        oracle_mod.build_lowcut(0.0, 0.01)
+
+
+# ----------------------------------------------------------------- FIR ------------
+
+@pytest.mark.parametrize("name", ["body", "maketest", "short"])
+def test_fir_matches_reference_filtercore_golden(oracle_mod, name):
+    g = golden(f"filtercore_{name}.npz")
+    x, taps = g["x"], g["taps"]
+    # ref_f32 mode == what FilterCore.h stores (float32), up to the summation order
+    # inside fms(), which lives in the absent c_lib: allow 1 float32 ulp.
+    y32 = oracle_mod.fir_f32(x, taps)
+    ulp = np.spacing(np.abs(g["y_full"]).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(y32.astype(np.float64) - g["y_full"]) <= ulp)
+    assert np.count_nonzero(y32 != g["y_full"]) <= 0.001 * x.size
+    # hi mode (long double accumulate, no narrowing) rounds to the same float32
+    # wherever it is not within a hair of a rounding boundary
+    yhi = oracle_mod.fir_hi(x.astype(np.float64), taps)
+    assert np.all(np.abs(yhi - g["y_full"]) <= 0.5 * ulp + 1e-12)
+    # a sub-range that starts in the prologue and ends in the epilogue
+    lo, hi = int(g["lo"]), int(g["hi"])
+    y_rng = oracle_mod.fir_f32(x, taps, lo, hi)
+    assert np.all(np.abs(y_rng[lo:hi].astype(np.float64) - g["y_rng"][lo:hi]) <= ulp[lo:hi])
+    assert not y_rng[:lo].any() and not y_rng[hi:].any()
+    # thread partition of ProcessFile.cp:64-69 does not change a single bit
+    assert np.array_equal(g["y_full"], g["y_thr"])
+    for nt in (1, 3, 5):
+        assert np.array_equal(oracle_mod.fir_f32(x, taps, threads=nt), y32)
+
+
+def test_fir_live_reference_build_agrees(oracle_mod):
+    """Where oracle/_ref exists (built from /root/reference here; travels to the GPU
+    box as a .so), rerun the reference's FilterCore.h live on a fresh signal."""
+    if oracle_mod.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    taps = oracle_mod.build_lowcut(30.0 / 44100, 300.0 / 44100)
+    x = rng.uniform(-1, 1, 4000).astype(np.float32)
+    y_ref = oracle_mod.ref_fir_f32(x, taps)
+    y32 = oracle_mod.fir_f32(x, taps)
+    ulp = np.spacing(np.abs(y_ref)).astype(np.float64)
+    assert np.all(np.abs(y32.astype(np.float64) - y_ref) <= ulp)
+
+
+def test_fir_impulse_constant_alternating(oracle_mod):
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000)
+    M = taps.size - 1
+    H = M // 2
+    N = 3000
+    # impulse at p -> y[n] = h[p - n + H]: the taps come back (reversed == same: symmetric)
+    x = np.zeros(N)
+    p = 1400
+    x[p] = 1.0
+    y = oracle_mod.fir_hi(x, taps)
+    assert np.array_equal(y[p - H:p + H + 1], taps[::-1])
+    assert not y[:p - H].any() and not y[p + H + 1:].any()
+    # constant -> 0 in the steady state (sum h = 0)
+    y = oracle_mod.fir_hi(np.full(N, 0.75), taps)
+    assert np.max(np.abs(y[H:N - H])) < 1e-16
+    assert np.max(np.abs(y[:H])) > 1e-3          # the edges see a step: not zero
+    # alternating +-1 -> gain ~ 1 at Nyquist
+    x = (-1.0) ** np.arange(N)
+    y = oracle_mod.fir_hi(x, taps)
+    assert np.max(np.abs(np.abs(y[H:N - H]) - 1.0)) < 1e-3
+
+
+@pytest.mark.parametrize("N", [1, 2, 17, 480, 481, 960, 961, 962, 2500])
+def test_fir_edges_equal_zero_padded_convolution(oracle_mod, N):
+    """FilterCore.h:57-76's three loops == the zero-padded full convolution, for any N
+    (the reference itself has UB for N < taps; the oracle implements the formula)."""
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000)
+    H = (taps.size - 1) // 2
+    rng = np.random.default_rng(N)
+    x = rng.uniform(-1, 1, N)
+    y = oracle_mod.fir_hi(x, taps)
+    full = np.convolve(x.astype(np.longdouble), taps[::-1].astype(np.longdouble))  # correlation
+    want = full[H:H + N].astype(np.float64)
+    scale = oracle_mod.fir_abs_scale(x, taps)
+    assert np.all(np.abs(y - want) <= 1e-15 * scale + 1e-300)
+
+
+def test_abs_scale_bounds(oracle_mod):
+    taps = oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000)
+    x = np.random.default_rng(1).uniform(-1, 1, 2000)
+    s = oracle_mod.fir_abs_scale(x, taps)
+    y = oracle_mod.fir_hi(x, taps)
+    assert np.all(np.abs(y) <= s * (1 + 1e-12))
+    assert np.all(s <= np.abs(taps).sum() * np.abs(x).max() * (1 + 1e-12))
+
+
+# --------------------------------------------------------------- codec ------------
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+@pytest.mark.parametrize("be", [False, True])
+def test_codec_round_trip_is_identity(oracle_mod, bits, be):
+    rng = np.random.default_rng(bits + be)
+    frames, ch = 257, 3
+    nb = bits // 8
+    lim = 1 << (bits - 1)
+    q = rng.integers(-lim, lim, size=(frames, ch), dtype=np.int64)
+    q[0, 0], q[1, 0], q[2, 0] = -lim, lim - 1, 0
+    b = np.zeros((frames, ch, nb), dtype=np.uint8)
+    for k in range(nb):
+        b[..., (nb - 1 - k) if be else k] = (q >> (8 * k)) & 0xFF
+    pcm = b.reshape(-1)
+    x = oracle_mod.decode(pcm, frames, ch, bits, be)
+    assert np.array_equal(x, (q / float(lim)).T)            # x = int / 2^(bits-1), exact
+    assert x.min() == -1.0 and x.max() == (lim - 1) / lim
+    back = oracle_mod.encode(x, 1.0, bits, be)
+    assert np.array_equal(back, pcm)
+    x32 = oracle_mod.decode(pcm, frames, ch, bits, be, dtype=np.float32)
+    assert np.array_equal(x32, x.astype(np.float32))
+
+
+def test_encode_rounding_and_clipping(oracle_mod):
+    lim = 1 << 15
+    # ties to even: 0.5 -> 0, 1.5 -> 2, 2.5 -> 2, -0.5 -> -0, -1.5 -> -2
+    y = np.array([[0.5, 1.5, 2.5, -0.5, -1.5, 0.49999, 3.0e4, 1.0, -1.0, 2.0, -2.0]]) / lim
+    y[0, 6:] = [0.999999, 1.0, -1.0, 2.0, -2.0]
+    pcm = oracle_mod.encode(y, 1.0, 16, False)
+    q = pcm.view("<i2")
+    assert list(q[:6]) == [0, 2, 2, 0, -2, 0]
+    assert list(q[6:]) == [32767, 32767, -32768, 32767, -32768]      # clamp, no wrap
+    q_be = oracle_mod.encode(y, 1.0, 16, True).view(">i2")
+    assert np.array_equal(q_be.astype(np.int16), q)
+
+
+def test_scale_rule(oracle_mod):
+    # ProcessFile.cp:98: maxMag > 1.0f || normalize
+    assert oracle_mod.scale_for_peak(0.5, False) == 1.0
+    assert oracle_mod.scale_for_peak(0.5, True) == 2.0
+    assert oracle_mod.scale_for_peak(1.0, False) == 1.0
+    assert oracle_mod.scale_for_peak(1.25, False) == 0.8
+    assert oracle_mod.scale_for_peak(0.0, True) == 1.0
+
+
+def test_peak(oracle_mod):
+    y = np.array([[0.1, -0.7, 0.3], [0.2, 0.69, -0.1]])
+    assert oracle_mod.peak(y) == 0.7
+
+
+# ---------------------------------------------------------- synthetic PCM ----------
+
+@pytest.mark.parametrize("bits,be", [(16, True), (24, False), (32, False)])
+def test_synth_pcm_is_counter_based_and_bounded(oracle_mod, bits, be):
+    ch, rate = 2, 48000
+    a = oracle_mod.synth_pcm(0xF1F1F1, 0, 5000, ch, bits, be, rate)
+    b = oracle_mod.synth_pcm(0xF1F1F1, 1000, 3000, ch, bits, be, rate)
+    fb = ch * bits // 8
+    assert np.array_equal(a[1000 * fb:4000 * fb], b)          # any window reproducible
+    x = oracle_mod.decode(a, 5000, ch, bits, be)
+    assert 0.3 < np.abs(x).max() < 0.9                         # auto-normalise does not fire
+    assert abs(x.mean() - 0.05) < 0.05                         # carries a DC offset to remove
+    loud = oracle_mod.decode(oracle_mod.synth_pcm(0xF1F1F1, 0, 5000, ch, bits, be, rate, gain=2.0), 5000, ch, bits, be)
+    assert np.abs(loud).max() > 0.99
+
+
+# ------------------------------------------------------------ whole path ----------
+
+def test_process_whole_path_and_halo_blocks(oracle_mod):
+    """oracle_process on the whole payload == per-block runs with (taps-1) halo and a
+    common scale: the property that makes sample-block sharding exact."""
+    fs, freq, slope = 8000, 40.0, 100.0
+    ch, bits, be, frames = 2, 24, False, 3000
+    pcm = oracle_mod.synth_pcm(1, 0, frames, ch, bits, be, fs, gain=1.0)
+    whole = oracle_mod.process(pcm, frames, ch, bits, be, freq / fs, slope / fs, True)
+    H = oracle_mod.kernel_order(slope / fs) // 2
+    assert whole["scale"] == 1.0 / whole["peak"]
+    fb = ch * bits // 8
+    out = np.empty_like(pcm)
+    peaks = []
+    cuts = [0, 1008, 2000, frames]
+    for s, e in zip(cuts[:-1], cuts[1:]):
+        hl, hr = min(H, s), min(H, frames - e)
+        r = oracle_mod.process(pcm[(s - hl) * fb:(e + hr) * fb], e - s, ch, bits, be, freq / fs, slope / fs,
+                               True, hl, hr)
+        assert np.array_equal(r["y"], whole["y"][:, s:e])
+        peaks.append(r["peak"])
+    assert max(peaks) == whole["peak"]
+    for s, e in zip(cuts[:-1], cuts[1:]):
+        hl, hr = min(H, s), min(H, frames - e)
+        r = oracle_mod.process(pcm[(s - hl) * fb:(e + hr) * fb], e - s, ch, bits, be, freq / fs, slope / fs,
+                               True, hl, hr, scale_in=1.0 / max(peaks))
+        out[s * fb:e * fb] = r["pcm"]
+    assert np.array_equal(out, whole["pcm"])
+    q = whole["pcm"].reshape(-1, 3)
+    v = (q[:, 0].astype(np.int32) | (q[:, 1].astype(np.int32) << 8) | (q[:, 2].astype(np.int8).astype(np.int32) << 16))
+    assert v.max() == (1 << 23) - 1 or v.min() == -(1 << 23)   # normalised to full scale

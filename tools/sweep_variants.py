@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""GPU tool: FP64 probes and a sweep of the FIR kernel variants on device-resident
+synthetic PCM (CUDA-event time of the FIR launches only).  Usage:
+    python tools/sweep_variants.py [--config 2] [--frames N] [--reps 3]"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from audio_fir_filter_b200 import capi  # noqa: E402
+from bench import CONFIGS, SEED, algorithmic_flop, kernel_order  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=2)
+ap.add_argument("--frames", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--variants", default="")
+a = ap.parse_args()
+cfg = CONFIGS[a.config]
+frames = a.frames or cfg["frames"]
+fs, ch, bits, be = cfg["fs"], cfg["channels"], cfg["bits"], cfg["be"]
+ctx = capi.Context(0)
+print(json.dumps({"dfma_tflops": ctx.fp64_peak(0, 0.3), "dmma_tflops": ctx.fp64_peak(1, 0.3)}), flush=True)
+k = ctx.build_kernel(cfg["freq"] / fs, cfg["slope"] / fs)
+taps = k.num_taps
+d = torch.empty(frames * ch * bits // 8, dtype=torch.uint8, device="cuda:0")
+ctx.synth_pcm_dev(SEED, 0, frames, ch, bits, be, fs, 1.0, d)
+flop = algorithmic_flop(frames, ch, taps, 0, 0)
+names = capi.variant_names()
+sel = [int(v) for v in a.variants.split(",")] if a.variants else range(len(names))
+for v in sel:
+    ctx.set_variant(v)
+    best = None
+    for _ in range(a.reps + 1):
+        ctx.apply_dev(k, d, frames, ch, bits, be)
+        t = ctx.last_timing()
+        best = t["fir_ms"] if best is None else min(best, t["fir_ms"])
+    print(json.dumps({"variant": v, "name": names[v], "fir_ms": best, "tflops": flop / best / 1e9,
+                      "decode_ms": t["decode_ms"], "peak": ctx.peak()}), flush=True)
