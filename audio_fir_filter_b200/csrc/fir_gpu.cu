@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 
+#include "fir_dmma.cuh"
 #include "fir_fp64.cuh"
 #include "pcm_codec.cuh"
 #include "sinc_kernel.cuh"
@@ -58,33 +59,60 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 // ---- FIR kernel variants ------------------------------------------------------
 
+typedef void (*DfmaFn)(const CUtensorMap, const double*, int, double*, long long, long long, unsigned long long*);
+typedef void (*DmmaFn)(const double*, long long, const double*, int, double*, long long, long long,
+                       unsigned long long*);
+
 struct FirVariant {
 	const char* name;
-	int nt, kt, stages, t_out, box_rows, smem;
-	void (*kernel)(const CUtensorMap, const double*, int, double*, long long, long long, unsigned long long*);
+	int dmma; // 0: DFMA kernel (fir_fp64.cuh), 1: DMMA kernel (fir_dmma.cuh)
+	int nt, kt, t_out, box_rows, smem;
+	DfmaFn dfma_kernel;
+	DmmaFn dmma_kernel;
 };
 
 template <class Cfg>
-FirVariant make_variant(const char* name)
+FirVariant dfma_variant(const char* name)
 {
-	return {name, Cfg::NT, Cfg::KT, Cfg::STAGES, Cfg::T_OUT, Cfg::BOX_ROWS, Cfg::SMEM_BYTES,
-	        fir_fp64_kernel<Cfg>};
+	return {name, 0, Cfg::NT, Cfg::KT, Cfg::T_OUT, Cfg::BOX_ROWS, Cfg::SMEM_BYTES, fir_fp64_kernel<Cfg>, nullptr};
 }
 
-constexpr int MAX_KT = 1024; // tap arrays are zero-padded to a multiple of this
+template <class Cfg>
+FirVariant dmma_variant(const char* name)
+{
+	return {name, 1, Cfg::NT, Cfg::KT, Cfg::T_OUT, 0, Cfg::SMEM_BYTES, nullptr, fir_dmma_kernel<Cfg>};
+}
+
+constexpr int MAX_KT = 1024; // tap arrays are zero-padded generously beyond any variant's tile
+constexpr int TAP_PAD = 8;   // zeros in front of h[0] (the DMMA Toeplitz blocks reach k = -7)
 
 const FirVariant* fir_variants(int* n)
 {
 	static const FirVariant v[] = {
-		make_variant<FirCfg<256, 512, 2, 2>>("nt256_kt512_s2_b2"),
-		make_variant<FirCfg<128, 512, 2, 4>>("nt128_kt512_s2_b4"),
-		make_variant<FirCfg<256, 512, 3, 1>>("nt256_kt512_s3_b1"),
-		make_variant<FirCfg<128, 256, 3, 4>>("nt128_kt256_s3_b4"),
-		make_variant<FirCfg<256, 1024, 2, 2>>("nt256_kt1024_s2_b2"),
-		make_variant<FirCfg<64, 512, 2, 8>>("nt64_kt512_s2_b8"),
+		dmma_variant<DmmaCfg<256, 3, 512, 2, 2>>("dmma_nt256_t3_kt512_s2_b2"),
+		dfma_variant<FirCfg<256, 512, 2, 2>>("dfma_nt256_kt512_s2_b2"),
+		dfma_variant<FirCfg<256, 512, 3, 1>>("dfma_nt256_kt512_s3_b1"),
+		dfma_variant<FirCfg<128, 512, 2, 4>>("dfma_nt128_kt512_s2_b4"),
+		dmma_variant<DmmaCfg<256, 2, 512, 2, 3>>("dmma_nt256_t2_kt512_s2_b3"),
+		dmma_variant<DmmaCfg<256, 4, 512, 2, 1>>("dmma_nt256_t4_kt512_s2_b1"),
+		dmma_variant<DmmaCfg<128, 3, 512, 2, 4>>("dmma_nt128_t3_kt512_s2_b4"),
+		dmma_variant<DmmaCfg<256, 3, 256, 3, 2>>("dmma_nt256_t3_kt256_s3_b2"),
+		dmma_variant<DmmaCfg<512, 3, 512, 2, 1>>("dmma_nt512_t3_kt512_s2_b1"),
 	};
 	*n = (int) (sizeof(v) / sizeof(v[0]));
 	return v;
+}
+
+const FirVariant& variant_of(const fir_gpu_ctx* c);
+
+// Doubles per channel the FIR of `frames` outputs may read from the padded input.
+int64_t x_pitch_for(const FirVariant& v, int64_t frames, int64_t n_taps)
+{
+	const int64_t H = (n_taps - 1) / 2;
+	if (!v.dmma) return (std::max<int64_t>(frames, 1) + 2 * H + 15) / 16 * 16;
+	const int64_t blocks = (std::max<int64_t>(frames, 1) + v.t_out - 1) / v.t_out;
+	const int64_t n_ktiles = (n_taps + 7 + v.kt - 1) / v.kt;
+	return blocks * v.t_out + n_ktiles * v.kt;
 }
 
 struct EventPair {
@@ -96,8 +124,9 @@ struct EventPair {
 struct fir_gpu_kernel {
 	int device = 0;
 	int64_t n_taps = 0;   // M + 1
-	int64_t n_padded = 0; // multiple of MAX_KT, zero tail
-	double* d_taps = nullptr;
+	int64_t n_alloc = 0;  // doubles allocated: TAP_PAD zeros, the taps, a zero tail
+	double* d_tpad = nullptr;
+	double* d_taps = nullptr; // = d_tpad + TAP_PAD
 };
 
 struct fir_gpu_ctx {
@@ -132,6 +161,13 @@ struct fir_gpu_ctx {
 };
 
 namespace {
+
+const FirVariant& variant_of(const fir_gpu_ctx* c)
+{
+	int nv = 0;
+	const FirVariant* vs = fir_variants(&nv);
+	return vs[(c->variant >= 0 && c->variant < nv) ? c->variant : 0];
+}
 
 struct DeviceGuard {
 	int prev = -1;
@@ -259,34 +295,40 @@ void launch_encode(fir_gpu_ctx* c, const double* y, int64_t y_pitch, int64_t fra
 		else { if (be) fn<32, true>(__VA_ARGS__); else fn<32, false>(__VA_ARGS__); } \
 	} while (0)
 
-// One FIR launch over a zero-padded planar chunk resident at d_x.
+// One FIR launch over a zero-padded planar chunk resident at d_x (pitch from x_pitch_for).
 int launch_fir(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* d_x, int64_t x_pitch, int ch, double* y,
                int64_t y_pitch, int64_t frames, unsigned long long* peak)
 {
 	int nv = 0;
 	const FirVariant* vs = fir_variants(&nv);
-	const FirVariant& v = vs[(c->variant >= 0 && c->variant < nv) ? c->variant : 0];
-
-	CUtensorMap map;
-	const cuuint64_t dims[3] = {16, (cuuint64_t) (x_pitch / 16), (cuuint64_t) ch};
-	const cuuint64_t strides[2] = {128, (cuuint64_t) x_pitch * 8};
-	const cuuint32_t box[3] = {16, (cuuint32_t) v.box_rows, 1};
-	const cuuint32_t estr[3] = {1, 1, 1};
-	CUresult r = c->encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) d_x, dims, strides, box, estr,
-	                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-	                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	if (r != CUDA_SUCCESS) return fail(FIR_GPU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int) r));
-
-	if ((int) c->fir_attr.size() < nv) c->fir_attr.assign(nv, 0);
+	const FirVariant& v = variant_of(c);
 	const int vi = (int) (&v - vs);
+	if ((int) c->fir_attr.size() < nv) c->fir_attr.assign(nv, 0);
 	if (!c->fir_attr[vi]) {
-		CU_TRY(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+		const void* fn = v.dmma ? (const void*) v.dmma_kernel : (const void*) v.dfma_kernel;
+		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
 		c->fir_attr[vi] = 1;
 	}
-	const int n_ktiles = (int) ((k->n_taps + v.kt - 1) / v.kt);
 	dim3 grid((unsigned) ((frames + v.t_out - 1) / v.t_out), (unsigned) ch);
-	v.kernel<<<grid, v.nt, v.smem, c->stream>>>(map, k->d_taps, n_ktiles, y, (long long) y_pitch, (long long) frames,
-	                                           peak);
+	if (v.dmma) {
+		const int n_ktiles = (int) ((k->n_taps + 7 + v.kt - 1) / v.kt);
+		v.dmma_kernel<<<grid, v.nt, v.smem, c->stream>>>(d_x, (long long) x_pitch, k->d_tpad, n_ktiles, y,
+		                                               (long long) y_pitch, (long long) frames, peak);
+	} else {
+		CUtensorMap map;
+		const cuuint64_t dims[3] = {16, (cuuint64_t) (x_pitch / 16), (cuuint64_t) ch};
+		const cuuint64_t strides[2] = {128, (cuuint64_t) x_pitch * 8};
+		const cuuint32_t box[3] = {16, (cuuint32_t) v.box_rows, 1};
+		const cuuint32_t estr[3] = {1, 1, 1};
+		CUresult r = c->encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) d_x, dims, strides, box, estr,
+		                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+		                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS)
+			return fail(FIR_GPU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int) r));
+		const int n_ktiles = (int) ((k->n_taps + v.kt - 1) / v.kt);
+		v.dfma_kernel<<<grid, v.nt, v.smem, c->stream>>>(map, k->d_taps, n_ktiles, y, (long long) y_pitch,
+		                                               (long long) frames, peak);
+	}
 	CU_TRY(cudaGetLastError());
 	c->fir_launches++;
 	return FIR_GPU_OK;
@@ -449,12 +491,15 @@ static int alloc_kernel(fir_gpu_ctx* c, int64_t n_taps, fir_gpu_kernel** out)
 	fir_gpu_kernel* k = new fir_gpu_kernel();
 	k->device = c->device;
 	k->n_taps = n_taps;
-	k->n_padded = round_up(n_taps, MAX_KT);
-	cudaError_t e = cudaMalloc(&k->d_taps, (size_t) k->n_padded * sizeof(double));
+	k->n_alloc = TAP_PAD + round_up(n_taps + 8, MAX_KT) + MAX_KT + 32;
+	cudaError_t e = cudaMalloc(&k->d_tpad, (size_t) k->n_alloc * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemsetAsync(k->d_tpad, 0, (size_t) k->n_alloc * sizeof(double), c->stream);
 	if (e != cudaSuccess) {
+		cudaFree(k->d_tpad);
 		delete k;
 		return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc taps: ") + cudaGetErrorString(e));
 	}
+	k->d_taps = k->d_tpad + TAP_PAD;
 	*out = k;
 	return FIR_GPU_OK;
 }
@@ -489,8 +534,7 @@ int fir_gpu_build_kernel(fir_gpu_ctx* c, double fc_norm, double bw_norm, fir_gpu
 	}
 	sinc_lowpass_kernel<<<blocks, 256, 0, c->stream>>>(M, fc_norm, d_lp, d_part);
 	sinc_sum_kernel<<<1, 256, 0, c->stream>>>(d_part, blocks, d_part + blocks);
-	sinc_lowcut_kernel<<<(unsigned) ((k->n_padded + 255) / 256), 256, 0, c->stream>>>(M, d_lp, d_part + blocks,
-	                                                                                 k->d_taps, k->n_padded);
+	sinc_lowcut_kernel<<<blocks, 256, 0, c->stream>>>(M, d_lp, d_part + blocks, k->d_taps, M + 1);
 	e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	cudaFree(d_lp);
@@ -516,11 +560,6 @@ int fir_gpu_kernel_from_taps(fir_gpu_ctx* c, const double* taps, int64_t n_taps,
 	if (rc) return rc;
 	cudaError_t e = cudaMemcpyAsync(k->d_taps, taps, (size_t) n_taps * sizeof(double), cudaMemcpyHostToDevice,
 	                                c->stream);
-	if (e == cudaSuccess && k->n_padded > n_taps) {
-		pad_taps_kernel<<<(unsigned) ((k->n_padded - n_taps + 255) / 256), 256, 0, c->stream>>>(k->d_taps, n_taps,
-		                                                                                       k->n_padded);
-		e = cudaGetLastError();
-	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) {
 		fir_gpu_kernel_free(k);
@@ -546,7 +585,7 @@ void fir_gpu_kernel_free(fir_gpu_kernel* k)
 {
 	if (!k) return;
 	DeviceGuard g(k->device);
-	cudaFree(k->d_taps);
+	cudaFree(k->d_tpad);
 	delete k;
 }
 
@@ -571,18 +610,16 @@ static int apply_dev_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* p
 	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
 
 	// chunk so that the decoded FP64 input stays within x_budget_bytes
-	int nv = 0;
-	const FirVariant* vs = fir_variants(&nv);
-	const int t_out = vs[c->variant].t_out;
-	int64_t chunk = c->x_budget_bytes / 8 / ch - 2 * H - 16;
-	chunk = chunk / t_out * t_out;
+	const FirVariant& v = variant_of(c);
+	const int t_out = v.t_out;
+	int64_t chunk = (c->x_budget_bytes / 8 / ch - (k->n_taps + 2 * MAX_KT)) / t_out * t_out;
 	if (chunk < t_out) chunk = t_out;
 	if (chunk > frames) chunk = frames;
 
 	const int64_t avail_lo = -fmt->halo_left, avail_hi = frames + fmt->halo_right;
 	for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
 		const int64_t nf = std::min(chunk, frames - f0);
-		const int64_t x_pitch = round_up(nf + 2 * H, 16);
+		const int64_t x_pitch = x_pitch_for(v, nf, k->n_taps);
 		rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
 		if (rc) return rc;
 		size_t s = begin_span(c);
@@ -637,7 +674,7 @@ int fir_gpu_filter_f64(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* x_
 	DeviceGuard g(c->device);
 	reset_timing(c, true);
 	const int64_t H = (k->n_taps - 1) / 2;
-	const int64_t x_pitch = round_up(frames + 2 * H, 16);
+	const int64_t x_pitch = x_pitch_for(variant_of(c), frames, k->n_taps);
 	c->parked = false;
 	c->y_pitch = round_up(frames, 16);
 	int rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * channels * sizeof(double));

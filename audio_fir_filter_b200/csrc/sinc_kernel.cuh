@@ -120,19 +120,14 @@ sinc_sum_kernel(const dd* __restrict__ partial, int n_partial, dd* __restrict__ 
 	if (threadIdx.x == 0) *sum_out = red[0];
 }
 
-// Pass 3: h[i] = -lp[i]/S (+1 at the centre), written into the zero-padded tap
-// array (n_padded >= M+1 entries; the tail is zero so whole tap tiles can be
-// fetched by the FIR without a remainder loop).
+// Pass 3: h[i] = -lp[i]/S (+1 at the centre) for i = 0..M.  The caller has
+// zero-filled the padded tap array around them.
 __global__ void __launch_bounds__(256)
 sinc_lowcut_kernel(long long M, const double* __restrict__ lp, const dd* __restrict__ sum,
-                   double* __restrict__ taps, long long n_padded)
+                   double* __restrict__ taps, long long n)
 {
 	const long long i = (long long) blockIdx.x * 256 + threadIdx.x;
-	if (i >= n_padded) return;
-	if (i > M) {
-		taps[i] = 0.0;
-		return;
-	}
+	if (i >= n) return;
 	const dd S = *sum;
 	const double h = lp[i];
 	// q = h / (S.hi + S.lo) as a double-double quotient
@@ -145,14 +140,6 @@ sinc_lowcut_kernel(long long M, const double* __restrict__ lp, const dd* __restr
 	} else {
 		taps[i] = -__dadd_rn(q0, q1);
 	}
-}
-
-// Zero-pad caller-supplied taps (fir_gpu_kernel_from_taps).
-__global__ void __launch_bounds__(256)
-pad_taps_kernel(double* __restrict__ taps, long long n, long long n_padded)
-{
-	const long long i = (long long) blockIdx.x * 256 + threadIdx.x + n;
-	if (i < n_padded) taps[i] = 0.0;
 }
 
 // ---- register-resident FP64 throughput probes --------------------------------
