@@ -334,11 +334,20 @@ def main() -> int:
             traffic = json.load(open(tpath)).get(f"cfg{a.config}")
         except Exception:
             traffic = None
+    vname = capi.variant_names()[a.variant if a.variant >= 0 else 0]
+    is_dmma = vname.startswith("dmma")
+    fp64_peak = dmma_peak if is_dmma else dfma_peak
     roofline = {
-        "kernel": "fir_fp64_kernel", "bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
-        "frac": achieved / dfma_peak, "traffic": traffic,
-        "peak_source": "measured live: register-resident DFMA probe (fir_gpu_fp64_peak kind 0); MEASURED_PEAKS.json "
-                       "has no FP64 figure",
+        "kernel": "fir_dmma_kernel" if is_dmma else "fir_fp64_kernel",
+        # the FP64 tensor pipe (DMMA.8x8x4) for the default kernel, the FP64 FMA pipe for the dfma_* variants
+        "bound": "tensor" if is_dmma else "fp64_fma",
+        "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp64_peak, "traffic": traffic,
+        "peak_source": "measured live on this GPU before the run: register-resident "
+                       + ("DMMA m8n8k4 f64 probe" if is_dmma else "DFMA probe")
+                       + " (fir_gpu_fp64_peak); MEASURED_PEAKS.json has no FP64 figure (its bf16 number is for "
+                         "tcgen05, which has no FP64 kind)",
+        "dfma_probe": dfma_peak,
         "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12, "dmma_probe": dmma_peak,
         "flop_per_launch": flop_launch, "fir_ms_per_launch": fir_avg_ms,
         "fir_share_of_step": fir_avg_ms / ms_per_step,
@@ -365,7 +374,7 @@ def main() -> int:
                 "big_endian": be, "normalize": cfg["normalize"], "sample_rate": fs,
                 "l2": "inputs larger than L2 (PCM + FP64 planes per step >> 126 MB)" if
                       (in_bytes + 16 * blk.frames * ch) > 200e6 else "working set may fit L2; see DESIGN.md",
-                "fir_variant": capi.variant_names()[a.variant if a.variant >= 0 else 0],
+                "fir_variant": vname,
             },
             "fp64_tflops": flop_launch * (world if a.mode == "block" else world) / (ms_per_step * 1e-3) / 1e12,
             "host_wall_ms_per_step": wall_ms / a.steps,
