@@ -1,0 +1,91 @@
+// lowcut -- command-line host of the B200 low-cut FIR (scenarios of the reference's
+// main.cp:84-148; exit codes and messages of its catch ladder :153-164).
+#include <cmath>
+#include <cstdlib>
+#include <filesystem>
+#include <format>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "errors.hpp"
+#include "options.hpp"
+#include "process_file.hpp"
+
+namespace fs = std::filesystem;
+using namespace lowcut;
+
+int main(int argc, char** argv)
+{
+	int exit_val = EXIT_SUCCESS;
+	try {
+		const CliOptions cli = parse_cli(argc, argv);
+		if (cli.help) throw StopNoError(help_text());             // main.cp:64-66
+
+		FilterOptions opts{cli.freq, cli.slope, cli.normalize, cli.verbose, cli.num_threads};
+		// main.cp:75-76 keeps a thread count even though nothing here uses it
+		if (opts.num_threads == 0) opts.num_threads = (unsigned) std::floor(std::thread::hardware_concurrency() * 0.7);
+		if (opts.num_threads == 0) opts.num_threads = 4;
+
+		std::vector<fs::path> paths(cli.paths.begin(), cli.paths.end());
+		if (paths.size() < 2) throw UsageError("Invalid number of parameters. Need at least 2.");   // main.cp:150
+		if (!(opts.slope > 0.0)) throw UsageError("Filter slope width must be greater than 0 Hz.");
+		if (!(opts.freq > 0.0)) throw UsageError("Filter cutoff frequency must be greater than 0 Hz.");
+
+		if (paths.size() == 2) {
+			// Scenario 1: input file -> output file (main.cp:84-110)
+			const fs::path& in = paths[0];
+			const fs::path& out = paths[1];
+			if (!fs::exists(in) || !fs::is_regular_file(in)) throw FileNotFound(in.string());
+			if (fs::exists(out) && fs::is_directory(out))
+				throw UsageError("With two parameters the second parameter must be a file path, not a directory.");
+			if (in.extension() != out.extension())
+				throw UsageError("Input and output file types (WAVE or AIFF) must be the same (extensions must match).");
+			if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
+			GpuPool pool(cli.gpus);
+			// main.cp:69-72 prints its resource line only when -v is NOT given; kept as is
+			if (!opts.verbose) std::cout << std::format("Using {} GPU(s).", pool.size()) << std::endl;
+			if (fs::exists(out)) fs::remove(out);
+			process_file(in, out, opts, pool);
+		} else {
+			// Scenario 2: input files -> output directory (main.cp:112-148)
+			const fs::path& dest = paths.back();
+			if (fs::exists(dest)) {
+				if (!fs::is_directory(dest))
+					throw UsageError(std::format("Destination exists but is not a directory: {}", dest.string()));
+			} else {
+				if (dest.has_extension())
+					throw UsageError(std::format(
+						"Destination directory '{}' does not exist and has a suffix. Undefined scenario.", dest.string()));
+				if (!opts.verbose) std::cout << std::format("Creating directory: {}", dest.string()) << std::endl;
+				fs::create_directories(dest);
+			}
+			// the reference validates each file as it reaches it (main.cp:132-147); the
+			// per-GPU workers run files concurrently, so validate them all up front
+			std::vector<std::pair<fs::path, fs::path>> jobs;
+			for (size_t i = 0; i + 1 < paths.size(); ++i) {
+				const fs::path& in = paths[i];
+				if (!fs::exists(in) || !fs::is_regular_file(in)) throw FileNotFound(in.string());
+				fs::path out = dest / in.filename();
+				if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
+				jobs.emplace_back(in, out);
+			}
+			GpuPool pool(cli.gpus);
+			if (!opts.verbose) std::cout << std::format("Using {} GPU(s).", pool.size()) << std::endl;
+			for (const auto& j : jobs)
+				if (fs::exists(j.second)) fs::remove(j.second);
+			process_batch(jobs, opts, pool);
+		}
+	} catch (const StopNoError& e) {
+		const std::string s = e.what();
+		if (!s.empty()) std::cout << s << std::endl;
+	} catch (const std::exception& e) {
+		std::cerr << e.what() << std::endl;
+		exit_val = EXIT_FAILURE;
+	} catch (...) {
+		std::cerr << "Caught an unknown exception." << std::endl;
+		exit_val = EXIT_FAILURE;
+	}
+	return exit_val;
+}

@@ -1,0 +1,54 @@
+// process_file.hpp -- per-file orchestration of the lowcut hot path on B200s.
+//
+// Mirrors the reference's ProcessFile.h (FilterOptions :13-19, process_file :21-25);
+// the arithmetic of ProcessFile.cp:41-101,117 runs behind the C-ABI of
+// include/fir_gpu.h, the container work of :34-35,105-116 stays here.
+#pragma once
+#include <filesystem>
+#include <memory>
+#include <utility>
+#include <vector>
+
+struct fir_gpu_ctx;
+
+namespace lowcut {
+
+struct FilterOptions {
+	double freq = 15.0;       // -f, Hz
+	double slope = 10.0;      // -s, Hz
+	bool normalize = false;   // -n
+	bool verbose = false;     // -v
+	unsigned num_threads = 0; // -t: accepted, unused (the device grid replaces the thread fan-out)
+};
+
+// One fir_gpu context per B200 in use.  Throws GpuError if there is none: this
+// program has no CPU path.
+class GpuPool {
+public:
+	explicit GpuPool(unsigned want /* 0 = all usable devices */);
+	~GpuPool();
+	GpuPool(const GpuPool&) = delete;
+	GpuPool& operator=(const GpuPool&) = delete;
+	size_t size() const { return ctx_.size(); }
+	fir_gpu_ctx* ctx(size_t i) const { return ctx_[i]; }
+
+private:
+	std::vector<fir_gpu_ctx*> ctx_;
+};
+
+// One file (ProcessFile.cp:27-120).  A file long enough is split into contiguous
+// sample blocks with (taps-1) halo across every GPU of the pool (one peak
+// max-reduction in between); a short one runs on the pool's first GPU.
+void process_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
+                  const FilterOptions& opts, GpuPool& pool);
+
+// Batch scenario (main.cp:132-147): whole files dealt to GPUs, one host worker
+// thread per device, no communication.  The first failure stops the hand-out of
+// further files and is rethrown once the files in flight are done.
+void process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
+                   const FilterOptions& opts, GpuPool& pool);
+
+// ProcessFile.cp:98: normalise when the peak exceeds full scale or -n is given.
+double scale_for_peak(double peak, bool normalize);
+
+} // namespace lowcut

@@ -1,0 +1,103 @@
+"""GPU tests of the C++23 host: `host/lowcut` end to end on real WAVE / AIFF files --
+sample payload against the oracle, every other byte identical to the input."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from audio_fixtures import aiff_bytes, wav_bytes
+from conftest import ROOT
+from test_gpu_parity import lsb_flips
+
+pytestmark = pytest.mark.gpu
+LOWCUT = os.path.join(ROOT, "host", "lowcut")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(LOWCUT):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+def run(*args):
+    return subprocess.run([LOWCUT, *map(str, args)], capture_output=True, text=True)
+
+
+def check_output(oracle_mod, src_bytes, out_bytes, pcm, ch, bits, be, fs, freq, slope, normalize):
+    off = src_bytes.index(pcm[:64])
+    n = len(pcm)
+    assert len(out_bytes) == len(src_bytes)
+    assert out_bytes[:off] == src_bytes[:off] and out_bytes[off + n:] == src_bytes[off + n:]   # non-audio bytes
+    frames = n // (ch * bits // 8)
+    want = oracle_mod.process(np.frombuffer(pcm, dtype=np.uint8), frames, ch, bits, be, freq / fs, slope / fs, normalize)
+    got = np.frombuffer(out_bytes[off:off + n], dtype=np.uint8)
+    nflip, mx = lsb_flips(got, want["pcm"], bits, be)
+    assert mx <= 1 and nflip <= 2 + 1e-5 * got.size, (nflip, mx)
+    return nflip
+
+
+def test_single_file_wave_24bit_with_foreign_chunks(tmp_path, oracle_mod):
+    fs, ch, bits, frames = 48000, 2, 24, 120_000
+    pcm = oracle_mod.synth_pcm(0xF1F1F1, 0, frames, ch, bits, False, fs).tobytes()
+    src = tmp_path / "in.wav"
+    data = wav_bytes(pcm, ch, bits, fs)
+    src.write_bytes(data)
+    dst = tmp_path / "out.wav"
+    r = run("-f", 20, "-s", 200, src, dst)
+    assert r.returncode == 0, r.stderr
+    assert "Processing file: in.wav" in r.stdout
+    check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, False, fs, 20.0, 200.0, False)
+    # existing output: refused without -O, replaced with it
+    assert run("-f", 20, "-s", 200, src, dst).returncode == 1
+    r = run("-O", "-v", "--frequency=20", "--slope", "200", "-n", src, dst)
+    assert r.returncode == 0, r.stderr
+    assert "Doing audio normalize." in r.stdout and "Writing output file." in r.stdout
+    check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, False, fs, 20.0, 200.0, True)
+
+
+def test_single_file_aiff_16bit_big_endian_normalize(tmp_path, oracle_mod):
+    fs, ch, bits, frames = 44100, 2, 16, 100_000
+    pcm = oracle_mod.synth_pcm(3, 0, frames, ch, bits, True, fs).tobytes()
+    data = aiff_bytes(pcm, ch, bits, float(fs), ssnd_offset=4)
+    src = tmp_path / "in.aif"
+    src.write_bytes(data)
+    dst = tmp_path / "out.aif"
+    r = run("-f", 30, "-s", 300, "-n", src, dst)
+    assert r.returncode == 0, r.stderr
+    check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, True, fs, 30.0, 300.0, True)
+
+
+def test_batch_mode_to_directory(tmp_path, oracle_mod):
+    fs = 48000
+    files = []
+    for i, (ch, bits) in enumerate([(2, 24), (1, 16), (4, 32), (2, 24)]):
+        pcm = oracle_mod.synth_pcm(100 + i, 0, 30_000 + 1000 * i, ch, bits, False, fs).tobytes()
+        p = tmp_path / f"f{i}.wav"
+        data = wav_bytes(pcm, ch, bits, fs, extensible=(bits == 32))
+        p.write_bytes(data)
+        files.append((p, data, pcm, ch, bits))
+    outdir = tmp_path / "filtered"
+    r = run("-f", 40, "-s", 400, *[f[0] for f in files], outdir)
+    assert r.returncode == 0, r.stderr
+    assert "Creating directory" in r.stdout
+    for p, data, pcm, ch, bits in files:
+        assert f"Processing file: {p.name}" in r.stdout
+        check_output(oracle_mod, data, (outdir / p.name).read_bytes(), pcm, ch, bits, False, fs, 40.0, 400.0, False)
+
+
+def test_sample_block_mode_across_gpus_equals_single_gpu(tmp_path, oracle_mod):
+    from audio_fir_filter_b200 import capi
+
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fs, ch, bits, frames = 48000, 2, 24, 700_000
+    pcm = oracle_mod.synth_pcm(5, 0, frames, ch, bits, False, fs).tobytes()
+    src = tmp_path / "long.wav"
+    src.write_bytes(wav_bytes(pcm, ch, bits, fs))
+    one, two = tmp_path / "one.wav", tmp_path / "two.wav"
+    assert run("-g", 1, "-f", 20, "-s", 100, "-n", src, one).returncode == 0
+    r = run("-g", 2, "-v", "-f", 20, "-s", 100, "-n", src, two)
+    assert r.returncode == 0 and "sample blocks" in r.stdout
+    assert one.read_bytes() == two.read_bytes()

@@ -1,0 +1,181 @@
+"""CPU tests of the C++23 host: the chunk-preserving container layer (through
+host/container_tool) and the CLI's validation / exit-code behaviour (main.cp:84-164).
+No GPU is touched: every error below is raised before a device is needed."""
+import json
+import os
+import subprocess
+import wave
+
+import numpy as np
+import pytest
+
+from audio_fixtures import aiff_bytes, wav_bytes
+from conftest import ROOT
+
+TOOL = os.path.join(ROOT, "host", "container_tool")
+LOWCUT = os.path.join(ROOT, "host", "lowcut")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def info(path):
+    r = subprocess.run([TOOL, "info", str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout)
+
+
+def rand_pcm(frames, channels, bits, seed=0):
+    return np.random.default_rng(seed).integers(0, 256, frames * channels * bits // 8, dtype=np.uint8).tobytes()
+
+
+CASES = [
+    ("plain16.wav", lambda p: wav_bytes(p, 2, 16, 44100, extra_before=False, extra_after=False), 2, 16, False, 44100),
+    ("chunks24.wav", lambda p: wav_bytes(p, 2, 24, 48000), 2, 24, False, 48000),
+    ("ext32.wav", lambda p: wav_bytes(p, 6, 32, 96000, extensible=True), 6, 32, False, 96000),
+    ("big.rf64.wav", lambda p: wav_bytes(p, 2, 24, 192000, rf64=True), 2, 24, False, 192000),
+    ("plain16.aif", lambda p: aiff_bytes(p, 2, 16, 44100.0), 2, 16, True, 44100),
+    ("offset24.aif", lambda p: aiff_bytes(p, 3, 24, 48000.0, ssnd_offset=6), 3, 24, True, 48000),
+    ("commlast32.aif", lambda p: aiff_bytes(p, 1, 32, 88200.0, comm_last=True), 1, 32, True, 88200),
+    ("sowt.aifc", lambda p: aiff_bytes(p, 2, 16, 22050.0, aifc=b"sowt"), 2, 16, False, 22050),
+    ("none.aifc", lambda p: aiff_bytes(p, 2, 24, 48000.0, aifc=b"NONE"), 2, 24, True, 48000),
+]
+
+
+@pytest.mark.parametrize("name,build,ch,bits,be,rate", CASES)
+def test_container_layout_and_byte_identity(tmp_path, name, build, ch, bits, be, rate):
+    frames = 1001                                   # odd payload sizes for 24-bit mono/3ch: pad byte
+    pcm = rand_pcm(frames, ch, bits, seed=len(name))
+    data = build(pcm)
+    src = tmp_path / name
+    src.write_bytes(data)
+    i = info(src)
+    assert (i["channels"], i["bits"], i["big_endian"], i["rate"], i["frames"]) == (ch, bits, be, rate, frames)
+    off, n = i["payload_offset"], i["payload_bytes"]
+    assert data[off:off + n] == pcm
+    assert i["file_size"] == len(data)
+    assert len(i["chunks"]) >= 2
+    # output = input outside the payload, byte for byte (ProcessFile.cp:107-117)
+    dst = tmp_path / ("out_" + name)
+    r = subprocess.run([TOOL, "invert", str(src), str(dst)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dst.read_bytes()
+    assert len(out) == len(data)
+    assert out[:off] == data[:off] and out[off + n:] == data[off + n:]
+    assert out[off:off + n] == bytes(b ^ 0xFF for b in pcm)
+
+
+def test_container_agrees_with_python_wave_module(tmp_path):
+    p = tmp_path / "std.wav"
+    with wave.open(str(p), "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(3)
+        w.setframerate(48000)
+        w.writeframes(rand_pcm(500, 2, 24))
+    i = info(p)
+    assert (i["type"], i["channels"], i["bits"], i["frames"], i["rate"]) == ("WAVE", 2, 24, 500, 48000)
+    # and the other way: what the tool writes is still a file the stdlib reads
+    q = tmp_path / "inv.wav"
+    assert subprocess.run([TOOL, "invert", str(p), str(q)]).returncode == 0
+    with wave.open(str(q), "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, 3, 48000, 500)
+
+
+def test_container_truncated_and_rejected_formats(tmp_path):
+    pcm = rand_pcm(100, 2, 16)
+    data = wav_bytes(pcm, 2, 16, 44100, extra_before=False, extra_after=False)
+    t = tmp_path / "trunc.wav"
+    t.write_bytes(data[:-51])                        # data chunk claims more than the file holds
+    assert info(t)["frames"] == (len(pcm) - 51) // 4
+    f = tmp_path / "float.wav"
+    f.write_bytes(data.replace(b"\x01\x00\x02\x00", b"\x03\x00\x02\x00", 1))   # format tag 3 = IEEE float
+    r = subprocess.run([TOOL, "info", str(f)], capture_output=True, text=True)
+    assert r.returncode == 1 and "not integer PCM" in r.stderr
+    e = tmp_path / "eight.wav"
+    e.write_bytes(wav_bytes(rand_pcm(10, 1, 8), 1, 8, 8000))
+    r = subprocess.run([TOOL, "info", str(e)], capture_output=True, text=True)
+    assert r.returncode == 1 and "16-, 24- and 32-bit" in r.stderr
+    g = tmp_path / "garbage.wav"
+    g.write_bytes(b"not an audio file at all")
+    r = subprocess.run([TOOL, "info", str(g)], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a WAVE or AIFF" in r.stderr
+
+
+# ---------------------------------------------------------------- CLI -------------
+
+def run(*args):
+    return subprocess.run([LOWCUT, *map(str, args)], capture_output=True, text=True)
+
+
+def test_cli_help_goes_to_stdout_with_success():
+    r = run("--help")                                 # StopNoError: main.cp:64-66,153-156
+    assert r.returncode == 0 and "Usage:" in r.stdout and "--frequency" in r.stdout and r.stderr == ""
+    assert run("-h").returncode == 0
+
+
+def test_cli_parameter_count_and_unknown_options():
+    r = run()
+    assert r.returncode == 1 and "Invalid number of parameters. Need at least 2." in r.stderr
+    assert run("only.wav").returncode == 1
+    r = run("--bogus", "a.wav", "b.wav")
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
+    r = run("-f")
+    assert r.returncode == 1 and "missing" in r.stderr
+    r = run("-f", "abc", "a.wav", "b.wav")
+    assert r.returncode == 1 and "invalid" in r.stderr
+
+
+def test_cli_single_file_scenario_validation(tmp_path):
+    src = tmp_path / "in.wav"
+    src.write_bytes(wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100))
+    r = run(tmp_path / "missing.wav", tmp_path / "out.wav")
+    assert r.returncode == 1 and "missing.wav" in r.stderr                       # FileNotFound
+    d = tmp_path / "dir.wav"
+    d.mkdir()
+    r = run(src, d)
+    assert r.returncode == 1 and "must be a file path, not a directory" in r.stderr
+    r = run(src, tmp_path / "out.aif")
+    assert r.returncode == 1 and "extensions must match" in r.stderr
+    existing = tmp_path / "exists.wav"
+    existing.write_bytes(b"keep me")
+    r = run(src, existing)
+    assert r.returncode == 1 and "exists.wav" in r.stderr                        # FileExists without -O
+    assert existing.read_bytes() == b"keep me"
+    r = run("-s", "0", src, tmp_path / "o.wav")
+    assert r.returncode == 1 and "slope" in r.stderr
+
+
+def test_cli_batch_scenario_validation(tmp_path):
+    a = tmp_path / "a.wav"
+    a.write_bytes(wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100))
+    b = tmp_path / "b.wav"
+    b.write_bytes(a.read_bytes())
+    notdir = tmp_path / "file.txt"
+    notdir.write_text("x")
+    r = run(a, b, notdir)
+    assert r.returncode == 1 and "Destination exists but is not a directory" in r.stderr
+    r = run(a, b, tmp_path / "newdir.out")
+    assert r.returncode == 1 and "does not exist and has a suffix" in r.stderr
+    outdir = tmp_path / "out"
+    outdir.mkdir()
+    r = run(a, tmp_path / "nope.wav", outdir)
+    assert r.returncode == 1 and "nope.wav" in r.stderr
+    (outdir / "a.wav").write_bytes(b"old")
+    r = run(a, b, outdir)
+    assert r.returncode == 1 and "a.wav" in r.stderr                             # FileExists
+    assert (outdir / "a.wav").read_bytes() == b"old"
+
+
+def test_cli_without_a_gpu_fails_loudly_never_falls_back(tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    src = tmp_path / "in.wav"
+    src.write_bytes(wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100))
+    r = run(src, tmp_path / "out.wav")
+    assert r.returncode == 1 and "no CPU path" in r.stderr
+    assert not (tmp_path / "out.wav").exists()
