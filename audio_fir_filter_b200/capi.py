@@ -82,6 +82,7 @@ SYMBOLS = {
     "fir_gpu_apply_dev": (C.c_int, [_vp, _vp, _vp, C.POINTER(PcmFormat)]),
     "fir_gpu_filter_f64": (C.c_int, [_vp, _vp, _dp, _i64, C.c_int32, _dp]),
     "fir_gpu_parked": (C.c_int, [_vp, _dp, _i64, C.c_int32]),
+    "fir_gpu_parked_range": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int32]),
     "fir_gpu_peak": (C.c_int, [_vp, _dp]),
     "fir_gpu_peak_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
     "fir_gpu_peak_recompute": (C.c_int, [_vp, _dp]),
@@ -257,6 +258,11 @@ class Context:
     def parked(self, frames: int, channels: int) -> np.ndarray:
         y = np.empty((channels, frames), dtype=np.float64)
         _check(lib().fir_gpu_parked(self._h, y.ctypes.data_as(_dp), frames, channels))
+        return y
+
+    def parked_range(self, first_frame: int, frames: int, channels: int) -> np.ndarray:
+        y = np.empty((channels, frames), dtype=np.float64)
+        _check(lib().fir_gpu_parked_range(self._h, y.ctypes.data_as(_dp), first_frame, frames, channels))
         return y
 
     def peak(self) -> float:

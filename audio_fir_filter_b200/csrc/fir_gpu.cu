@@ -712,6 +712,20 @@ int fir_gpu_parked(fir_gpu_ctx* c, double* y_host, int64_t frames, int32_t chann
 	return FIR_GPU_OK;
 }
 
+int fir_gpu_parked_range(fir_gpu_ctx* c, double* y_host, int64_t first_frame, int64_t frames, int32_t channels)
+{
+	if (!c || !y_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on this context");
+	if (channels != c->fmt.channels || first_frame < 0 || frames < 0 || first_frame + frames > c->fmt.frames)
+		return fail(FIR_GPU_ERR_INVALID, "window does not lie inside the parked signal");
+	DeviceGuard g(c->device);
+	if (frames)
+		CU_TRY(cudaMemcpy2DAsync(y_host, (size_t) frames * 8, c->d_y + first_frame, (size_t) c->y_pitch * 8,
+		                         (size_t) frames * 8, (size_t) channels, cudaMemcpyDeviceToHost, c->stream));
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
 // -------------------------------------------------------------------- peak
 
 int fir_gpu_peak(fir_gpu_ctx* c, double* peak)

@@ -139,6 +139,11 @@ FIR_GPU_API int fir_gpu_filter_f64(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, co
 /* Copy the parked FP64 signal, planar [channels][frames], to the host. */
 FIR_GPU_API int fir_gpu_parked(fir_gpu_ctx *ctx, double *y_host, int64_t frames, int32_t channels);
 
+/* A window of it: frames [first_frame, first_frame + frames) of every channel,
+ * planar [channels][frames] (spot checks of files too large to copy back whole). */
+FIR_GPU_API int fir_gpu_parked_range(fir_gpu_ctx *ctx, double *y_host, int64_t first_frame, int64_t frames,
+                                     int32_t channels);
+
 /* ---- fir_gpu_peak  (ProcessFile.cp:92-96) -------------------------------- */
 
 /* max over channels and frames of |y| of the parked signal on THIS device.
