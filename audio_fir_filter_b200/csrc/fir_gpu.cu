@@ -98,6 +98,12 @@ const FirVariant* fir_variants(int* n)
 		dmma_variant<DmmaCfg<128, 3, 512, 2, 4>>("dmma_nt128_t3_kt512_s2_b4"),
 		dmma_variant<DmmaCfg<256, 3, 256, 3, 2>>("dmma_nt256_t3_kt256_s3_b2"),
 		dmma_variant<DmmaCfg<512, 3, 512, 2, 1>>("dmma_nt512_t3_kt512_s2_b1"),
+		dmma_variant<DmmaCfg<128, 2, 512, 2, 6>>("dmma_nt128_t2_kt512_s2_b6"),
+		dmma_variant<DmmaCfg<256, 2, 256, 3, 3>>("dmma_nt256_t2_kt256_s3_b3"),
+		dmma_variant<DmmaCfg<128, 2, 256, 3, 6>>("dmma_nt128_t2_kt256_s3_b6"),
+		dmma_variant<DmmaCfg<256, 2, 512, 3, 3>>("dmma_nt256_t2_kt512_s3_b3"),
+		dmma_variant<DmmaCfg<256, 2, 1024, 2, 3>>("dmma_nt256_t2_kt1024_s2_b3"),
+		dmma_variant<DmmaCfg<192, 2, 512, 2, 4>>("dmma_nt192_t2_kt512_s2_b4"),
 	};
 	*n = (int) (sizeof(v) / sizeof(v[0]));
 	return v;
@@ -133,6 +139,8 @@ struct fir_gpu_ctx {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // H2D of the next chunk runs under the FIR of the current one
+	cudaEvent_t copy_done = nullptr, pcm_free = nullptr;
 	PFN_encodeTiled encode_tiled = nullptr;
 
 	unsigned char* d_pcm = nullptr;
@@ -205,7 +213,7 @@ int ensure(void** p, size_t* cap, size_t need)
 	return FIR_GPU_OK;
 }
 
-size_t begin_span(fir_gpu_ctx* c)
+size_t begin_span(fir_gpu_ctx* c, cudaStream_t st = nullptr)
 {
 	if (c->pool_used == c->pool.size()) {
 		EventPair p;
@@ -213,11 +221,11 @@ size_t begin_span(fir_gpu_ctx* c)
 		cudaEventCreate(&p.b);
 		c->pool.push_back(p);
 	}
-	cudaEventRecord(c->pool[c->pool_used].a, c->stream);
+	cudaEventRecord(c->pool[c->pool_used].a, st ? st : c->stream);
 	return c->pool_used++;
 }
 
-void end_span(fir_gpu_ctx* c, size_t i) { cudaEventRecord(c->pool[i].b, c->stream); }
+void end_span(fir_gpu_ctx* c, size_t i, cudaStream_t st = nullptr) { cudaEventRecord(c->pool[i].b, st ? st : c->stream); }
 
 void reset_timing(fir_gpu_ctx* c, bool all)
 {
@@ -387,6 +395,9 @@ int fir_gpu_create(int device, fir_gpu_ctx** out)
 	c->sm_count = prop.multiProcessorCount;
 	CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
+	CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+	CU_TRY(cudaEventCreateWithFlags(&c->pcm_free, cudaEventDisableTiming));
 	CU_TRY(cudaMalloc(&c->d_peak, 64));
 	CU_TRY(cudaMemset(c->d_peak, 0, 64));
 	CU_TRY(cudaMalloc(&c->d_sink, 8));
@@ -418,6 +429,9 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 	cudaFree(c->d_peak);
 	cudaFree(c->d_sink);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->copy_done) cudaEventDestroy(c->copy_done);
+	if (c->pcm_free) cudaEventDestroy(c->pcm_free);
 	delete c;
 }
 
@@ -591,40 +605,74 @@ void fir_gpu_kernel_free(fir_gpu_kernel* k)
 
 // ------------------------------------------------------------------- apply
 
-static int apply_dev_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_dev, const fir_gpu_pcm* fmt)
+// The chunks of one apply: [f0, f0+nf) output frames each.  Every chunk fits the
+// decoded-input budget; on the host path the first chunk is a short one, so that the
+// upload of everything else hides under its FIR (and under the FIRs that follow).
+static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c, const FirVariant& v, int64_t frames,
+                                                            int ch, int64_t n_taps, bool from_host)
 {
-	int rc = check_fmt(fmt);
-	if (rc) return rc;
-	if (!pcm_dev && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
-	if (k->device != c->device) return fail(FIR_GPU_ERR_STATE, "kernel lives on another device");
-	DeviceGuard g(c->device);
+	const int64_t t_out = v.t_out;
+	int64_t chunk = (c->x_budget_bytes / 8 / ch - (n_taps + 2 * MAX_KT)) / t_out * t_out;
+	if (chunk < t_out) chunk = t_out;
+	std::vector<std::pair<int64_t, int64_t>> out;
+	int64_t f0 = 0;
+	if (from_host && frames >= 256 * t_out) {
+		const int64_t first = std::min(chunk, round_up(frames / 16, t_out));
+		out.emplace_back(0, first);
+		f0 = first;
+	}
+	for (; f0 < frames; f0 += chunk) out.emplace_back(f0, std::min(chunk, frames - f0));
+	return out;
+}
 
+// pcm_dev: interleaved PCM in device memory, first byte = frame -halo_left.
+// pcm_host != null: pcm_dev is the context's staging buffer, still empty; the bytes
+// are uploaded range by range on the copy stream just ahead of the chunk that
+// needs them.
+static int apply_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned char* pcm_dev, const fir_gpu_pcm* fmt,
+                      const unsigned char* pcm_host)
+{
+	if (k->device != c->device) return fail(FIR_GPU_ERR_STATE, "kernel lives on another device");
 	const int64_t H = (k->n_taps - 1) / 2;
 	const int ch = fmt->channels;
 	const int64_t frames = fmt->frames;
+	const size_t fb = (size_t) ch * (fmt->bits / 8);
 	c->parked = false;
 	c->fmt = *fmt;
 	c->y_pitch = round_up(std::max<int64_t>(frames, 1), 16);
-	rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * ch * sizeof(double));
+	int rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * ch * sizeof(double));
 	if (rc) return rc;
 	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
 
-	// chunk so that the decoded FP64 input stays within x_budget_bytes
 	const FirVariant& v = variant_of(c);
-	const int t_out = v.t_out;
-	int64_t chunk = (c->x_budget_bytes / 8 / ch - (k->n_taps + 2 * MAX_KT)) / t_out * t_out;
-	if (chunk < t_out) chunk = t_out;
-	if (chunk > frames) chunk = frames;
-
 	const int64_t avail_lo = -fmt->halo_left, avail_hi = frames + fmt->halo_right;
-	for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
-		const int64_t nf = std::min(chunk, frames - f0);
+	int64_t uploaded = avail_lo; // logical frame up to which the PCM is (being) uploaded
+	if (pcm_host) {
+		// the staging buffer may still be read by earlier work of the compute stream
+		CU_TRY(cudaEventRecord(c->pcm_free, c->stream));
+		CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->pcm_free, 0));
+	}
+	for (const auto& [f0, nf] : plan_chunks(c, v, frames, ch, k->n_taps, pcm_host != nullptr)) {
+		if (pcm_host) {
+			const int64_t need = std::min(avail_hi, f0 + nf + H);
+			if (need > uploaded) {
+				const size_t off = (size_t) (uploaded - avail_lo) * fb, n = (size_t) (need - uploaded) * fb;
+				size_t s = begin_span(c, c->copy_stream);
+				CU_TRY(cudaMemcpyAsync(const_cast<unsigned char*>(pcm_dev) + off, pcm_host + off, n,
+				                       cudaMemcpyHostToDevice, c->copy_stream));
+				end_span(c, s, c->copy_stream);
+				c->t_h2d.push_back(s);
+				CU_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+				CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+				uploaded = need;
+			}
+		}
 		const int64_t x_pitch = x_pitch_for(v, nf, k->n_taps);
 		rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
 		if (rc) return rc;
 		size_t s = begin_span(c);
-		DISPATCH_CODEC(launch_decode, fmt->bits, fmt->big_endian != 0, c, (const unsigned char*) pcm_dev, avail_lo,
-		               avail_hi, f0 - H, x_pitch, ch, c->d_x, x_pitch);
+		DISPATCH_CODEC(launch_decode, fmt->bits, fmt->big_endian != 0, c, pcm_dev, avail_lo, avail_hi, f0 - H, x_pitch,
+		               ch, c->d_x, x_pitch);
 		end_span(c, s);
 		c->t_decode.push_back(s);
 		c->other_launches++;
@@ -634,6 +682,10 @@ static int apply_dev_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* p
 		end_span(c, s);
 		c->t_fir.push_back(s);
 		if (rc) return rc;
+	}
+	if (pcm_host && uploaded < avail_hi) {
+		// frames beyond the last chunk's reach (halo_right longer than H): not needed
+		uploaded = avail_hi;
 	}
 	c->parked = true;
 	return FIR_GPU_OK;
@@ -651,18 +703,18 @@ int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host,
 	const size_t in_bytes = (size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fb;
 	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, in_bytes + 32);
 	if (rc) return rc;
-	size_t s = begin_span(c);
-	if (in_bytes) CU_TRY(cudaMemcpyAsync(c->d_pcm, pcm_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
-	end_span(c, s);
-	c->t_h2d.push_back(s);
-	return apply_dev_impl(c, k, c->d_pcm, fmt);
+	return apply_impl(c, k, c->d_pcm, fmt, static_cast<const unsigned char*>(pcm_host));
 }
 
 int fir_gpu_apply_dev(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_dev, const fir_gpu_pcm* fmt)
 {
 	if (!c || !k) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	int rc = check_fmt(fmt);
+	if (rc) return rc;
+	if (!pcm_dev && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
+	DeviceGuard g(c->device);
 	reset_timing(c, true);
-	return apply_dev_impl(c, k, pcm_dev, fmt);
+	return apply_impl(c, k, static_cast<const unsigned char*>(pcm_dev), fmt, nullptr);
 }
 
 int fir_gpu_filter_f64(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* x_host, int64_t frames,
