@@ -394,3 +394,30 @@ def test_error_behaviour(ctx):
     assert ctx.peak() == 0.0
     ctx.encode(1.0, pcm)
     k.free()
+
+
+def test_halo_semantics_missing_halo_is_zero_extra_halo_is_ignored(ctx, oracle_mod):
+    """fir_gpu_pcm.halo_left/right: real frames either side of the block; whatever is missing
+    up to half_len is implicit zero (a true file edge, FilterCore.h:57-61,72-76), anything
+    beyond half_len is accepted and ignored."""
+    fs, ch, bits, be = 8000, 2, 24, False
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)                 # 641 taps, H = 320
+    H = k.half_len
+    total = 6000
+    pcm = oracle_mod.synth_pcm(4, 0, total, ch, bits, be, fs)
+    fb = ch * bits // 8
+    taps = k.taps()
+    x = oracle_mod.decode(pcm, total, ch, bits, be)
+    s, e = 2000, 3504
+    for hl, hr in [(H, H), (H + 123, H + 77), (100, 50), (0, 0), (H, 0)]:
+        lo, hi = s - hl, e + hr
+        ctx.apply(k, pcm[lo * fb:hi * fb], e - s, ch, bits, be, hl, hr)
+        y = ctx.parked(e - s, ch)
+        for c in range(ch):
+            xx = np.zeros(total)
+            a, b = max(lo, s - H), min(hi, e + H)              # what the device may use
+            xx[a:b] = x[c, a:b]
+            want = oracle_mod.fir_hi(xx, taps, s, e)[s:e]
+            scale = oracle_mod.fir_abs_scale(xx, taps, s, e)[s:e]
+            assert np.all(np.abs(y[c] - want) <= TOL * scale + 1e-300), (hl, hr)
+    k.free()
