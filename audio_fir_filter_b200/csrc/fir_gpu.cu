@@ -266,7 +266,7 @@ void launch_decode(fir_gpu_ctx* c, const unsigned char* pcm, int64_t avail_lo, i
 {
 	const int fb = ch * (BITS / 8);
 	const int F = codec_tile_frames(fb);
-	const size_t smem = (size_t) F * fb + 64;
+	const size_t smem = codec_smem_bytes(F * fb);
 	bool& attr_done = c->codec_attr[(BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
 	if (!attr_done) {
 		cudaFuncSetAttribute(pcm_decode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
@@ -283,7 +283,7 @@ void launch_encode(fir_gpu_ctx* c, const double* y, int64_t y_pitch, int64_t fra
 {
 	const int fb = ch * (BITS / 8);
 	const int F = codec_tile_frames(fb);
-	const size_t smem = (size_t) F * fb + 64;
+	const size_t smem = codec_smem_bytes(F * fb);
 	bool& attr_done = c->codec_attr[6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
 	if (!attr_done) {
 		cudaFuncSetAttribute(pcm_encode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);

@@ -26,13 +26,25 @@ __host__ __device__ inline int codec_tile_frames(int fb)
 	return f < 32 ? 32 : f;
 }
 
-// 4 bytes at an arbitrary byte offset of a word-aligned smem tile, packed
-// little-endian (byte at `off` in bits 0..7).
+// The shared tile keeps the interleaved bytes in a SKEWED layout: one pad word after
+// every 32 (word w lives at w + w/32).  Lanes of the planar pass are 2*frame_bytes
+// apart; for wide frames (16 ch x 32 bit = 64 B) that is a multiple of 128 B and would
+// put all 32 lanes on one bank -- with the skew every power-of-two stride is
+// conflict-free, and so are the four word stores of a 16-byte chunk per lane.
+__host__ __device__ inline uint32_t pad_word(uint32_t w) { return w + (w >> 5); }
+__host__ __device__ inline uint32_t pad_byte(uint32_t b) { return b + ((b >> 7) << 2); }
+__host__ __device__ inline size_t codec_smem_bytes(int tile_bytes)
+{
+	return (size_t) pad_byte((uint32_t) tile_bytes + 64u) + 16u;
+}
+
+// 4 bytes at an arbitrary byte offset of the skewed tile, packed little-endian
+// (byte at `off` in bits 0..7).
 __device__ __forceinline__ uint32_t lds_unaligned_u32(const uint32_t* tile, uint32_t off)
 {
 	const uint32_t w = off >> 2;
-	const uint32_t lo = tile[w];
-	const uint32_t hi = tile[w + 1];
+	const uint32_t lo = tile[pad_word(w)];
+	const uint32_t hi = tile[pad_word(w + 1)];
 	return __funnelshift_r(lo, hi, (off & 3u) << 3);
 }
 
@@ -57,6 +69,38 @@ __device__ __forceinline__ uint32_t int_to_pcm(int32_t q)
 	if (BITS == 16) return BE ? __byte_perm(u, 0, 0x4401) : (u & 0xffffu);
 	if (BITS == 24) return BE ? __byte_perm(u, 0, 0x4012) : (u & 0xffffffu);
 	return BE ? __byte_perm(u, 0, 0x0123) : u;
+}
+
+// NB bytes of u (little-endian order, already endian-arranged) at logical byte offset
+// b of the skewed tile, with the widest stores the alignment allows (an aligned
+// 2- or 4-byte piece never straddles a pad).
+template <int NB>
+__device__ __forceinline__ void store_pcm_bytes(unsigned char* tile, uint32_t b, uint32_t u)
+{
+	if (NB == 2) {
+		if (!(b & 1)) *reinterpret_cast<uint16_t*>(tile + pad_byte(b)) = (uint16_t) u;
+		else {
+			tile[pad_byte(b)] = (unsigned char) u;
+			tile[pad_byte(b + 1)] = (unsigned char) (u >> 8);
+		}
+	} else if (NB == 4) {
+		if (!(b & 3)) *reinterpret_cast<uint32_t*>(tile + pad_byte(b)) = u;
+		else if (!(b & 1)) {
+			*reinterpret_cast<uint16_t*>(tile + pad_byte(b)) = (uint16_t) u;
+			*reinterpret_cast<uint16_t*>(tile + pad_byte(b + 2)) = (uint16_t) (u >> 16);
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) tile[pad_byte(b + k)] = (unsigned char) (u >> (8 * k));
+		}
+	} else {
+		if (!(b & 1)) {
+			*reinterpret_cast<uint16_t*>(tile + pad_byte(b)) = (uint16_t) u;
+			tile[pad_byte(b + 2)] = (unsigned char) (u >> 16);
+		} else {
+			tile[pad_byte(b)] = (unsigned char) u;
+			*reinterpret_cast<uint16_t*>(tile + pad_byte(b + 1)) = (uint16_t) (u >> 8);
+		}
+	}
 }
 
 // Decode a window of the interleaved PCM into the zero-padded planar layout.
@@ -92,10 +136,15 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 		for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
 			const uint32_t lo = v << 4, hi = lo + 16;
 			if (lo >= mis && hi <= end) {
-				reinterpret_cast<uint4*>(tile)[v] = __ldg(reinterpret_cast<const uint4*>(base + lo));
+				const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + lo)); // 128-bit coalesced
+				uint32_t* d = reinterpret_cast<uint32_t*>(tile) + pad_word(v << 2);
+				d[0] = q.x;
+				d[1] = q.y;
+				d[2] = q.z;
+				d[3] = q.w;
 			} else { // ragged head / tail: never touch bytes outside the payload
 				const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
-				for (uint32_t s = lo; s < hi; ++s) tile[s] = (s >= a && s < b) ? base[s] : 0;
+				for (uint32_t s = lo; s < hi; ++s) tile[pad_byte(s)] = (s >= a && s < b) ? base[s] : 0;
 			}
 		}
 	}
@@ -103,18 +152,24 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 
 	const double inv = 1.0 / (double) (1ll << (BITS - 1));
 	const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-	const int total = F * channels;
-	for (int idx = threadIdx.x; idx < total; idx += CODEC_NT) {
-		const int c = idx / F, fl = idx - c * F;
-		const long long i = i0 + fl;
-		if (i >= n_x) continue;
-		const long long g = g0 + i;
-		double v = 0.0;
-		if (g >= ga && g < gb) {
-			const uint32_t off = mis + (uint32_t) (g - ga) * fb + c * NB;
-			v = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, off)) * inv;
+	// Planar pass: channel by channel, a thread converts two consecutive frames and
+	// stores them with one 128-bit write (i0 and x_pitch are even, so the pair is
+	// 16-byte aligned).  No division in the loop.
+	const int la = (int) (ga - g0 - i0), lb = (int) (gb - g0 - i0); // tile-local frames present in pcm
+	int nloc = F;
+	if (i0 + nloc > n_x) nloc = (int) (n_x - i0);
+	for (int c = 0; c < channels; ++c) {
+		double* xc = x + (long long) c * x_pitch + i0;
+		const uint32_t cbase = mis + (uint32_t) c * NB - (uint32_t) la * fb;
+		for (int fl = 2 * threadIdx.x; fl < nloc; fl += 2 * CODEC_NT) {
+			double v0 = 0.0, v1 = 0.0;
+			if (fl >= la && fl < lb)
+				v0 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) fl * fb)) * inv;
+			if (fl + 1 >= la && fl + 1 < lb)
+				v1 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) (fl + 1) * fb)) * inv;
+			if (fl + 1 < nloc) *reinterpret_cast<double2*>(xc + fl) = make_double2(v0, v1);
+			else xc[fl] = v0;
 		}
-		x[(long long) c * x_pitch + i] = v;
 	}
 }
 
@@ -139,16 +194,28 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 	const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
 	const double hi_lim = (double) ((1ll << (BITS - 1)) - 1), lo_lim = -(double) (1ll << (BITS - 1));
 
-	const int total = F * channels;
-	for (int idx = threadIdx.x; idx < total; idx += CODEC_NT) {
-		const int c = idx / F, fl = idx - c * F;
-		if (fl >= nf) continue;
-		double v = y[(long long) c * y_pitch + f0 + fl] * gain;
-		v = fmin(fmax(v, lo_lim), hi_lim);
-		const uint32_t u = int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v));
-		unsigned char* d = tile + mis + (uint32_t) fl * fb + c * NB;
-#pragma unroll
-		for (int b = 0; b < NB; ++b) d[b] = (unsigned char) (u >> (8 * b));
+	// Planar pass: channel by channel, a thread quantises two consecutive frames
+	// (one 128-bit load when both exist) and drops their bytes into the tile.
+	for (int c = 0; c < channels; ++c) {
+		const double* yc = y + (long long) c * y_pitch + f0;
+		const uint32_t dc = mis + (uint32_t) c * NB;
+		for (int fl = 2 * threadIdx.x; fl < nf; fl += 2 * CODEC_NT) {
+			double v0, v1 = 0.0;
+			const bool two = fl + 1 < nf;
+			if (two) {
+				const double2 v = *reinterpret_cast<const double2*>(yc + fl);
+				v0 = v.x;
+				v1 = v.y;
+			} else {
+				v0 = yc[fl];
+			}
+			v0 = fmin(fmax(v0 * gain, lo_lim), hi_lim);
+			v1 = fmin(fmax(v1 * gain, lo_lim), hi_lim);
+			store_pcm_bytes<NB>(tile, dc + (uint32_t) fl * fb, int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v0)));
+			if (two)
+				store_pcm_bytes<NB>(tile, dc + (uint32_t) (fl + 1) * fb,
+				                    int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v1)));
+		}
 	}
 	__syncthreads();
 
@@ -158,10 +225,11 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 	for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
 		const uint32_t lo = v << 4, hi = lo + 16;
 		if (lo >= mis && hi <= end) {
-			*reinterpret_cast<uint4*>(base + lo) = reinterpret_cast<const uint4*>(tile)[v];
+			const uint32_t* q = reinterpret_cast<const uint32_t*>(tile) + pad_word(v << 2);
+			*reinterpret_cast<uint4*>(base + lo) = make_uint4(q[0], q[1], q[2], q[3]); // 128-bit coalesced
 		} else {
 			const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
-			for (uint32_t s = a; s < b; ++s) base[s] = tile[s];
+			for (uint32_t s = a; s < b; ++s) base[s] = tile[pad_byte(s)];
 		}
 	}
 }
