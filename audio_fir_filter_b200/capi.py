@@ -80,6 +80,11 @@ SYMBOLS = {
     "fir_gpu_kernel_free": (None, [_vp]),
     "fir_gpu_apply": (C.c_int, [_vp, _vp, _vp, C.POINTER(PcmFormat)]),
     "fir_gpu_apply_dev": (C.c_int, [_vp, _vp, _vp, C.POINTER(PcmFormat)]),
+    "fir_gpu_apply_begin": (C.c_int, [_vp, _vp, C.POINTER(PcmFormat)]),
+    "fir_gpu_apply_feed": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fir_gpu_apply_end": (C.c_int, [_vp]),
+    "fir_gpu_set_progress": (C.c_int, [_vp, _vp, _vp]),
+    "fir_gpu_encode_range": (C.c_int, [_vp, C.c_double, _i64, _i64, _vp]),
     "fir_gpu_filter_f64": (C.c_int, [_vp, _vp, _dp, _i64, C.c_int32, _dp]),
     "fir_gpu_parked": (C.c_int, [_vp, _dp, _i64, C.c_int32]),
     "fir_gpu_parked_range": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int32]),
@@ -244,6 +249,33 @@ class Context:
                   halo_left: int = 0, halo_right: int = 0) -> None:
         fmt = self._fmt(frames, channels, bits, big_endian, halo_left, halo_right)
         _check(lib().fir_gpu_apply_dev(self._h, kernel._h, _ptr(pcm_dev) or None, C.byref(fmt)))
+
+    def apply_streamed(self, kernel: Kernel, pieces, frames: int, channels: int, bits: int, big_endian: bool,
+                       halo_left: int = 0, halo_right: int = 0) -> None:
+        """fir_gpu_apply_begin / _feed / _end: ``pieces`` is an iterable of host byte buffers that,
+        concatenated, are the buffer fir_gpu_apply would receive."""
+        fmt = self._fmt(frames, channels, bits, big_endian, halo_left, halo_right)
+        _check(lib().fir_gpu_apply_begin(self._h, kernel._h, C.byref(fmt)))
+        keep = []
+        for p in pieces:
+            keep.append(p)          # keep the last two alive while their copies may be in flight
+            keep = keep[-2:]
+            n = p.nbytes if isinstance(p, np.ndarray) else len(p)
+            _check(lib().fir_gpu_apply_feed(self._h, _ptr(p) if n else None, n))
+        _check(lib().fir_gpu_apply_end(self._h))
+
+    def set_progress(self, fn) -> None:
+        """fn(done_frames, total_frames) or None.  Called from a CUDA callback thread."""
+        if fn is None:
+            self._progress_cb = None
+            _check(lib().fir_gpu_set_progress(self._h, None, None))
+            return
+        proto = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_void_p)
+        self._progress_cb = proto(lambda d, t, u: fn(d, t))
+        _check(lib().fir_gpu_set_progress(self._h, C.cast(self._progress_cb, _vp), None))
+
+    def encode_range(self, scale: float, first_frame: int, frames: int, out) -> None:
+        _check(lib().fir_gpu_encode_range(self._h, float(scale), first_frame, frames, _ptr(out) or None))
 
     def filter_f64(self, kernel: Kernel, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -124,6 +124,13 @@ struct EventPair {
 
 } // namespace
 
+// one pending progress callback (cudaLaunchHostFunc payload)
+struct ProgressNote {
+	fir_gpu_progress_fn fn;
+	void* user;
+	int64_t done, total;
+};
+
 struct fir_gpu_kernel {
 	int device = 0;
 	int64_t n_taps = 0;   // M + 1
@@ -137,7 +144,7 @@ struct fir_gpu_ctx {
 	int sm_count = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // H2D of the next chunk runs under the FIR of the current one
-	cudaEvent_t copy_done = nullptr, pcm_free = nullptr;
+	cudaEvent_t copy_done = nullptr, pcm_free = nullptr, feed_last = nullptr;
 	PFN_encodeTiled encode_tiled = nullptr;
 
 	unsigned char* d_pcm = nullptr;
@@ -150,6 +157,21 @@ struct fir_gpu_ctx {
 	double* d_sink = nullptr;
 
 	bool parked = false;
+
+	// the apply in progress (fir_gpu_apply_begin .. _end; fir_gpu_apply is begin + feed + end)
+	struct Pass {
+		bool active = false, from_host = false;
+		const fir_gpu_kernel* k = nullptr;
+		const unsigned char* pcm_dev = nullptr; // interleaved PCM on the device, byte 0 = frame -halo_left
+		std::vector<std::pair<int64_t, int64_t>> chunks; // (first output frame, frames)
+		size_t next = 0;       // next chunk to launch
+		size_t bytes_fed = 0;  // of the host payload, uploaded or in flight
+		size_t bytes_total = 0;
+		int64_t done_frames = 0;
+	} pass;
+	fir_gpu_progress_fn progress = nullptr;
+	void* progress_user = nullptr;
+	std::vector<ProgressNote*> notes;
 	fir_gpu_pcm fmt{};
 	int64_t y_pitch = 0;
 	int variant = 0;
@@ -395,6 +417,7 @@ int fir_gpu_create(int device, fir_gpu_ctx** out)
 	CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
 	CU_TRY(cudaEventCreateWithFlags(&c->pcm_free, cudaEventDisableTiming));
+	CU_TRY(cudaEventCreateWithFlags(&c->feed_last, cudaEventDisableTiming));
 	CU_TRY(cudaMalloc(&c->d_peak, 64));
 	CU_TRY(cudaMemset(c->d_peak, 0, 64));
 	CU_TRY(cudaMalloc(&c->d_sink, 8));
@@ -429,6 +452,8 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->copy_done) cudaEventDestroy(c->copy_done);
 	if (c->pcm_free) cudaEventDestroy(c->pcm_free);
+	if (c->feed_last) cudaEventDestroy(c->feed_last);
+	for (ProgressNote* n : c->notes) delete n;
 	delete c;
 }
 
@@ -603,72 +628,104 @@ void fir_gpu_kernel_free(fir_gpu_kernel* k)
 // ------------------------------------------------------------------- apply
 
 // The chunks of one apply: [f0, f0+nf) output frames each.  Every chunk fits the
-// decoded-input budget; on the host path the first chunk is a short one, so that the
-// upload of everything else hides under its FIR (and under the FIRs that follow).
+// decoded-input budget.  From host memory the first chunk is a short one, so that the
+// upload of everything else hides under its FIR (and under the FIRs that follow);
+// a streamed apply (feed by feed) is cut into ~16 chunks that start as their bytes land.
 static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c, const FirVariant& v, int64_t frames,
-                                                            int ch, int64_t n_taps, bool from_host)
+                                                            int ch, int64_t n_taps, int mode /*0 dev,1 host,2 stream*/)
 {
 	const int64_t t_out = v.t_out;
 	int64_t chunk = (c->x_budget_bytes / 8 / ch - (n_taps + 2 * MAX_KT)) / t_out * t_out;
 	if (chunk < t_out) chunk = t_out;
 	std::vector<std::pair<int64_t, int64_t>> out;
 	int64_t f0 = 0;
-	if (from_host && frames >= 256 * t_out) {
+	if (mode == 1 && frames >= 256 * t_out) {
 		const int64_t first = std::min(chunk, round_up(frames / 16, t_out));
 		out.emplace_back(0, first);
 		f0 = first;
 	}
+	if (mode == 2 && frames >= 256 * t_out) chunk = std::min(chunk, round_up(frames / 16, t_out));
 	for (; f0 < frames; f0 += chunk) out.emplace_back(f0, std::min(chunk, frames - f0));
 	return out;
 }
 
-// pcm_dev: interleaved PCM in device memory, first byte = frame -halo_left.
-// pcm_host != null: pcm_dev is the context's staging buffer, still empty; the bytes
-// are uploaded range by range on the copy stream just ahead of the chunk that
-// needs them.
-static int apply_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned char* pcm_dev, const fir_gpu_pcm* fmt,
-                      const unsigned char* pcm_host)
+static void CUDART_CB progress_trampoline(void* p)
+{
+	const ProgressNote* n = static_cast<const ProgressNote*>(p);
+	n->fn(n->done, n->total, n->user); // runs on a CUDA callback thread: no CUDA calls in there
+}
+
+static int pass_begin(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned char* pcm_dev, const fir_gpu_pcm* fmt,
+                      int mode)
 {
 	if (k->device != c->device) return fail(FIR_GPU_ERR_STATE, "kernel lives on another device");
-	const int64_t H = (k->n_taps - 1) / 2;
 	const int ch = fmt->channels;
 	const int64_t frames = fmt->frames;
-	const size_t fb = (size_t) ch * (fmt->bits / 8);
 	c->parked = false;
 	c->fmt = *fmt;
 	c->y_pitch = round_up(std::max<int64_t>(frames, 1), 16);
 	int rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * ch * sizeof(double));
 	if (rc) return rc;
 	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
+	for (ProgressNote* n : c->notes) delete n; // the previous pass has been synchronised by its peak / encode
+	c->notes.clear();
 
-	const FirVariant& v = variant_of(c);
-	const int64_t avail_lo = -fmt->halo_left, avail_hi = frames + fmt->halo_right;
-	int64_t uploaded = avail_lo; // logical frame up to which the PCM is (being) uploaded
-	if (pcm_host) {
+	fir_gpu_ctx::Pass& p = c->pass;
+	p = fir_gpu_ctx::Pass();
+	p.active = true;
+	p.from_host = mode != 0;
+	p.k = k;
+	p.pcm_dev = pcm_dev;
+	p.chunks = plan_chunks(c, variant_of(c), frames, ch, k->n_taps, mode);
+	p.bytes_total = (size_t) (fmt->halo_left + frames + fmt->halo_right) * ch * (fmt->bits / 8);
+	if (p.from_host) {
 		// the staging buffer may still be read by earlier work of the compute stream
 		CU_TRY(cudaEventRecord(c->pcm_free, c->stream));
 		CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->pcm_free, 0));
 	}
-	for (const auto& [f0, nf] : plan_chunks(c, v, frames, ch, k->n_taps, pcm_host != nullptr)) {
-		if (pcm_host) {
-			const int64_t need = std::min(avail_hi, f0 + nf + H);
-			if (need > uploaded) {
-				const size_t off = (size_t) (uploaded - avail_lo) * fb, n = (size_t) (need - uploaded) * fb;
-				size_t s = begin_span(c, c->copy_stream);
-				CU_TRY(cudaMemcpyAsync(const_cast<unsigned char*>(pcm_dev) + off, pcm_host + off, n,
-				                       cudaMemcpyHostToDevice, c->copy_stream));
-				end_span(c, s, c->copy_stream);
-				c->t_h2d.push_back(s);
-				CU_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
-				CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
-				uploaded = need;
-			}
+	return FIR_GPU_OK;
+}
+
+// Upload the next n bytes of the payload on the copy stream.
+static int pass_upload(fir_gpu_ctx* c, const unsigned char* src, size_t n)
+{
+	fir_gpu_ctx::Pass& p = c->pass;
+	if (!n) return FIR_GPU_OK;
+	size_t s = begin_span(c, c->copy_stream);
+	CU_TRY(cudaMemcpyAsync(const_cast<unsigned char*>(p.pcm_dev) + p.bytes_fed, src, n, cudaMemcpyHostToDevice,
+	                       c->copy_stream));
+	end_span(c, s, c->copy_stream);
+	c->t_h2d.push_back(s);
+	p.bytes_fed += n;
+	return FIR_GPU_OK;
+}
+
+// Launch decode + FIR of every chunk whose samples (incl. halo) have been uploaded.
+static int pass_launch_ready(fir_gpu_ctx* c)
+{
+	fir_gpu_ctx::Pass& p = c->pass;
+	const fir_gpu_pcm& fmt = c->fmt;
+	const fir_gpu_kernel* k = p.k;
+	const FirVariant& v = variant_of(c);
+	const int ch = fmt.channels;
+	const size_t fb = (size_t) ch * (fmt.bits / 8);
+	const int64_t H = (k->n_taps - 1) / 2;
+	const int64_t avail_lo = -fmt.halo_left, avail_hi = fmt.frames + fmt.halo_right;
+	const int64_t uploaded = p.from_host ? avail_lo + (int64_t) (p.bytes_fed / fb) : avail_hi;
+	bool waited = false;
+	while (p.next < p.chunks.size()) {
+		const auto [f0, nf] = p.chunks[p.next];
+		if (std::min(avail_hi, f0 + nf + H) > uploaded) break;
+		if (p.from_host && !waited) {
+			CU_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+			CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+			waited = true;
 		}
 		const int64_t x_pitch = x_pitch_for(v, nf, k->n_taps);
-		rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
+		int rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
 		if (rc) return rc;
 		size_t s = begin_span(c);
-		DISPATCH_CODEC(launch_decode, fmt->bits, fmt->big_endian != 0, c, pcm_dev, avail_lo, avail_hi, f0 - H, x_pitch,
+		DISPATCH_CODEC(launch_decode, fmt.bits, fmt.big_endian != 0, c, p.pcm_dev, avail_lo, avail_hi, f0 - H, x_pitch,
 		               ch, c->d_x, x_pitch);
 		end_span(c, s);
 		c->t_decode.push_back(s);
@@ -679,19 +736,41 @@ static int apply_impl(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned ch
 		end_span(c, s);
 		c->t_fir.push_back(s);
 		if (rc) return rc;
+		p.done_frames = f0 + nf;
+		if (c->progress) {
+			ProgressNote* n = new ProgressNote{c->progress, c->progress_user, p.done_frames, fmt.frames};
+			c->notes.push_back(n);
+			CU_TRY(cudaLaunchHostFunc(c->stream, progress_trampoline, n));
+		}
+		++p.next;
 	}
-	if (pcm_host && uploaded < avail_hi) {
-		// frames beyond the last chunk's reach (halo_right longer than H): not needed
-		uploaded = avail_hi;
+	return FIR_GPU_OK;
+}
+
+static int pass_end(fir_gpu_ctx* c)
+{
+	fir_gpu_ctx::Pass& p = c->pass;
+	if (p.from_host && p.bytes_fed != p.bytes_total) {
+		p.active = false;
+		return fail(FIR_GPU_ERR_STATE, "fir_gpu_apply_end: " + std::to_string(p.bytes_fed) + " of " +
+		                                   std::to_string(p.bytes_total) + " payload bytes were fed");
 	}
+	int rc = pass_launch_ready(c);
+	p.active = false;
+	if (rc) return rc;
 	c->parked = true;
 	return FIR_GPU_OK;
 }
 
-int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host, const fir_gpu_pcm* fmt)
+static int check_apply_args(fir_gpu_ctx* c, const fir_gpu_kernel* k, const fir_gpu_pcm* fmt)
 {
 	if (!c || !k) return fail(FIR_GPU_ERR_INVALID, "null argument");
-	int rc = check_fmt(fmt);
+	return check_fmt(fmt);
+}
+
+int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host, const fir_gpu_pcm* fmt)
+{
+	int rc = check_apply_args(c, k, fmt);
 	if (rc) return rc;
 	if (!pcm_host && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
 	DeviceGuard g(c->device);
@@ -700,18 +779,86 @@ int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host,
 	const size_t in_bytes = (size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fb;
 	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, in_bytes + 32);
 	if (rc) return rc;
-	return apply_impl(c, k, c->d_pcm, fmt, static_cast<const unsigned char*>(pcm_host));
+	rc = pass_begin(c, k, c->d_pcm, fmt, 1);
+	if (rc) return rc;
+	// upload range by range, just ahead of the chunk that needs it
+	const int64_t H = (k->n_taps - 1) / 2;
+	const unsigned char* src = static_cast<const unsigned char*>(pcm_host);
+	for (const auto& [f0, nf] : c->pass.chunks) {
+		const int64_t need = std::min(fmt->frames + fmt->halo_right, f0 + nf + H) + fmt->halo_left; // frames from byte 0
+		const size_t upto = std::min(in_bytes, (size_t) need * fb);
+		if (upto > c->pass.bytes_fed) {
+			rc = pass_upload(c, src + c->pass.bytes_fed, upto - c->pass.bytes_fed);
+			if (!rc) rc = pass_launch_ready(c);
+			if (rc) return rc;
+		}
+	}
+	if (c->pass.bytes_fed < in_bytes) { // halo_right beyond half_len: not needed by any chunk
+		rc = pass_upload(c, src + c->pass.bytes_fed, in_bytes - c->pass.bytes_fed);
+		if (rc) return rc;
+	}
+	return pass_end(c);
 }
 
 int fir_gpu_apply_dev(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_dev, const fir_gpu_pcm* fmt)
 {
-	if (!c || !k) return fail(FIR_GPU_ERR_INVALID, "null argument");
-	int rc = check_fmt(fmt);
+	int rc = check_apply_args(c, k, fmt);
 	if (rc) return rc;
 	if (!pcm_dev && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
 	DeviceGuard g(c->device);
 	reset_timing(c, true);
-	return apply_impl(c, k, static_cast<const unsigned char*>(pcm_dev), fmt, nullptr);
+	rc = pass_begin(c, k, static_cast<const unsigned char*>(pcm_dev), fmt, 0);
+	if (rc) return rc;
+	return pass_end(c);
+}
+
+// ---- streamed apply: the payload arrives piece by piece (file reads overlap the GPU) ----
+
+int fir_gpu_apply_begin(fir_gpu_ctx* c, const fir_gpu_kernel* k, const fir_gpu_pcm* fmt)
+{
+	int rc = check_apply_args(c, k, fmt);
+	if (rc) return rc;
+	DeviceGuard g(c->device);
+	reset_timing(c, true);
+	const size_t in_bytes =
+		(size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fmt->channels * (fmt->bits / 8);
+	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, in_bytes + 32);
+	if (rc) return rc;
+	return pass_begin(c, k, c->d_pcm, fmt, 2);
+}
+
+int fir_gpu_apply_feed(fir_gpu_ctx* c, const void* pcm_host, size_t bytes)
+{
+	if (!c || (!pcm_host && bytes)) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->pass.active || !c->pass.from_host) return fail(FIR_GPU_ERR_STATE, "no streamed apply is open");
+	if (c->pass.bytes_fed + bytes > c->pass.bytes_total)
+		return fail(FIR_GPU_ERR_INVALID, "more bytes fed than the format announced");
+	DeviceGuard g(c->device);
+	// the copy of the PREVIOUS feed must be done before the caller reuses that buffer
+	// (two alternating host buffers then never wait on the copy in flight)
+	CU_TRY(cudaEventSynchronize(c->feed_last));
+	int rc = pass_upload(c, static_cast<const unsigned char*>(pcm_host), bytes);
+	if (rc) return rc;
+	CU_TRY(cudaEventRecord(c->feed_last, c->copy_stream));
+	return pass_launch_ready(c);
+}
+
+int fir_gpu_apply_end(fir_gpu_ctx* c)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	if (!c->pass.active) return fail(FIR_GPU_ERR_STATE, "no streamed apply is open");
+	DeviceGuard g(c->device);
+	// the caller's last buffers are free once the copies are done
+	CU_TRY(cudaStreamSynchronize(c->copy_stream));
+	return pass_end(c);
+}
+
+int fir_gpu_set_progress(fir_gpu_ctx* c, fir_gpu_progress_fn fn, void* user)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	c->progress = fn;
+	c->progress_user = user;
+	return FIR_GPU_OK;
 }
 
 int fir_gpu_filter_f64(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* x_host, int64_t frames,
@@ -855,6 +1002,35 @@ int fir_gpu_encode(fir_gpu_ctx* c, double scale, void* pcm_host)
 	if (rc) return rc;
 	size_t s = begin_span(c);
 	if (out_bytes) CU_TRY(cudaMemcpyAsync(pcm_host, c->d_pcm, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+	end_span(c, s);
+	c->t_d2h.push_back(s);
+	CU_TRY(cudaStreamSynchronize(c->stream));
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_encode_range(fir_gpu_ctx* c, double scale, int64_t first_frame, int64_t frames, void* pcm_host)
+{
+	if (!c || !pcm_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (!c->parked || c->fmt.bits == 0) return fail(FIR_GPU_ERR_STATE, "no PCM-format signal is parked on this context");
+	if (!(scale > 0.0) || !std::isfinite(scale)) return fail(FIR_GPU_ERR_INVALID, "scale must be finite and > 0");
+	if (first_frame < 0 || frames < 0 || first_frame + frames > c->fmt.frames || (first_frame & 1))
+		return fail(FIR_GPU_ERR_INVALID, "range must lie inside the parked signal and start on an even frame");
+	DeviceGuard g(c->device);
+	const size_t fb = (size_t) c->fmt.channels * (c->fmt.bits / 8);
+	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, (size_t) c->fmt.frames * fb + 32);
+	if (rc) return rc;
+	if (frames == 0) return FIR_GPU_OK;
+	unsigned char* dst = c->d_pcm + (size_t) first_frame * fb;
+	const double gain = scale * std::ldexp(1.0, c->fmt.bits - 1);
+	size_t s = begin_span(c);
+	DISPATCH_CODEC(launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->d_y + first_frame, c->y_pitch, frames,
+	               c->fmt.channels, gain, dst);
+	end_span(c, s);
+	c->t_encode.push_back(s);
+	c->other_launches++;
+	CU_TRY(cudaGetLastError());
+	s = begin_span(c);
+	CU_TRY(cudaMemcpyAsync(pcm_host, dst, (size_t) frames * fb, cudaMemcpyDeviceToHost, c->stream));
 	end_span(c, s);
 	c->t_d2h.push_back(s);
 	CU_TRY(cudaStreamSynchronize(c->stream));

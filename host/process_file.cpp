@@ -9,6 +9,8 @@
 #include <mutex>
 #include <thread>
 
+#include <unistd.h>
+
 #include "../include/fir_gpu.h"
 #include "audio_container.hpp"
 #include "errors.hpp"
@@ -89,6 +91,94 @@ std::vector<Block> plan_blocks(int64_t total, size_t world, int64_t half_len)
 	return b;
 }
 
+// Text progress bar on stdout, driven by the library's per-chunk completion callback
+// (the reference drives ProgressBar.h:18-55 from apply_filter_range, FilterCore.h:38-54).
+// Only drawn on a terminal, so logs and pipes stay clean.
+struct Progress {
+	std::atomic<int64_t> done{0};
+	int64_t total = 0;
+	bool tty = false;
+	int last_pct = -1;
+	void draw()
+	{
+		if (!tty || total <= 0) return;
+		const int pct = (int) (100.0 * (double) done.load() / (double) total);
+		std::lock_guard<std::mutex> l(g_io);
+		if (pct == last_pct) return;
+		last_pct = pct;
+		const int w = 60, fill = pct * w / 100;
+		std::cout << '\r' << '[' << std::string(fill, '#') << std::string(w - fill, ' ') << "] " << pct << "%" << std::flush;
+		if (pct >= 100) std::cout << std::endl;
+	}
+};
+
+struct BlockProgress {
+	Progress* bar;
+	int64_t last = 0;
+};
+
+extern "C" void on_chunk_done(int64_t done_frames, int64_t, void* user)
+{
+	auto* b = static_cast<BlockProgress*>(user);
+	b->bar->done += done_frames - b->last;
+	b->last = done_frames;
+	b->bar->draw();
+}
+
+constexpr uint64_t PIECE_BYTES = 64ull << 20; // file <-> pinned buffer <-> device granularity
+
+// One sample block of the file on one GPU, streamed: file reads overlap upload and FIR.
+void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContainer& in, const Block& b, double* peak,
+                  Progress* bar)
+{
+	const PcmLayout& l = in.pcm();
+	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
+	const fir_gpu_pcm fmt = make_fmt(l, b.frames, b.halo_l, b.halo_r);
+	BlockProgress bp{bar};
+	check(fir_gpu_set_progress(ctx, on_chunk_done, &bp), "fir_gpu_set_progress");
+	check(fir_gpu_apply_begin(ctx, k, &fmt), "fir_gpu_apply_begin");
+	const uint64_t first = (uint64_t) (b.start - b.halo_l) * fb, total = (uint64_t) (b.halo_l + b.frames + b.halo_r) * fb;
+	PinnedBytes buf0(std::min(total, PIECE_BYTES)), buf1(std::min(total, PIECE_BYTES));
+	unsigned char* bufs[2] = {buf0.p, buf1.p};
+	int i = 0;
+	for (uint64_t off = 0; off < total; off += PIECE_BYTES, i ^= 1) {
+		const uint64_t n = std::min(PIECE_BYTES, total - off);
+		in.read_payload(first + off, n, bufs[i]);              // while the previous piece uploads / filters
+		check(fir_gpu_apply_feed(ctx, bufs[i], n), "fir_gpu_apply_feed");
+	}
+	check(fir_gpu_apply_end(ctx), "fir_gpu_apply_end");
+	check(fir_gpu_peak(ctx, peak), "fir_gpu_peak");            // ProcessFile.cp:92-96; waits for the FIR
+	fir_gpu_set_progress(ctx, nullptr, nullptr);
+}
+
+// Encode the block with the common scale and write it into the output's sample chunk,
+// piece by piece: the file write of one piece overlaps the encode + download of the next.
+void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double scale, int out_fd)
+{
+	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
+	const int64_t piece = std::max<int64_t>(2, (int64_t) (PIECE_BYTES / fb) & ~(int64_t) 1);
+	PinnedBytes buf0((uint64_t) std::min(piece, b.frames) * fb), buf1((uint64_t) std::min(piece, b.frames) * fb);
+	unsigned char* bufs[2] = {buf0.p, buf1.p};
+	std::thread writer;
+	std::exception_ptr werr;
+	int i = 0;
+	for (int64_t f = 0; f < b.frames; f += piece, i ^= 1) {
+		const int64_t n = std::min(piece, b.frames - f);
+		check(fir_gpu_encode_range(ctx, scale, f, n, bufs[i]), "fir_gpu_encode_range");
+		if (writer.joinable()) writer.join(); // the other buffer is on its way to the file
+		if (werr) std::rethrow_exception(werr);
+		writer = std::thread([&, f, n, i] {
+			try {
+				AudioContainer::write_payload(out_fd, l, (uint64_t) (b.start + f) * fb, (uint64_t) n * fb, bufs[i]);
+			} catch (...) {
+				werr = std::current_exception();
+			}
+		});
+	}
+	if (writer.joinable()) writer.join();
+	if (werr) std::rethrow_exception(werr);
+}
+
 void run_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
               const FilterOptions& opts, const std::vector<fir_gpu_ctx*>& ctxs)
 {
@@ -103,90 +193,78 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 	status(std::format("  {} {} ch, {} bit {}, {} Hz, {} frames, {} chunks", in.type_name(), l.channels, l.bits,
 	                   l.big_endian ? "big-endian" : "little-endian", l.sample_rate, l.frames, in.chunks().size()));
 	if (!(l.sample_rate > 0.0)) throw FormatError(input_path.string() + ": sample rate is zero");
-
-	status("Reading samples.");                                      // ProcessFile.cp:39-41
-	PinnedBytes pcm(l.payload_bytes);
-	in.read_payload(0, l.payload_bytes, pcm.p);
-
-	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
 	const double fc = opts.freq / l.sample_rate, bw = opts.slope / l.sample_rate; // ProcessFile.cp:48-49
 
 	// sample-block mode only pays when every GPU gets a sizeable block
 	size_t world = ctxs.size();
 	if (world > 1 && (int64_t) l.frames < (int64_t) world * (1 << 18)) world = 1;
 
+	// the output starts as a copy of every non-sample byte (ProcessFile.cp:104-112);
+	// done first so that it overlaps nothing it could disturb
+	status("Reading samples.");                                      // ProcessFile.cp:39-41 (streamed below)
 	status("Creating sinc kernel for this file's sample rate.");
 	double scale = 1.0, peak = 0.0;
-	if (l.frames > 0 && world == 1) {
-		fir_gpu_ctx* ctx = ctxs[0];
-		KernelHandle k(ctx, fc, bw);
-		status(std::format("  {} taps", fir_gpu_kernel_num_taps(k.k)));
-		status("Filtering.");
-		const fir_gpu_pcm fmt = make_fmt(l, (int64_t) l.frames, 0, 0);
-		check(fir_gpu_apply(ctx, k.k, pcm.p, &fmt), "fir_gpu_apply");
-		check(fir_gpu_peak(ctx, &peak), "fir_gpu_peak");             // ProcessFile.cp:92-96
-		scale = scale_for_peak(peak, opts.normalize);                // ProcessFile.cp:98-101
-		if (scale != 1.0) status("Doing audio normalize.");
-		check(fir_gpu_encode(ctx, scale, pcm.p), "fir_gpu_encode");  // the H2D copy is complete: reuse the buffer
-		status(timing_line(ctx));
-	} else if (l.frames > 0) {
-		// contiguous sample blocks with (taps-1) halo, one host thread per GPU
+	int out_fd = -1;
+	if (l.frames > 0) {
 		std::vector<std::unique_ptr<KernelHandle>> ks(world);
 		for (size_t r = 0; r < world; ++r) ks[r] = std::make_unique<KernelHandle>(ctxs[r], fc, bw);
 		const std::vector<Block> blocks = plan_blocks((int64_t) l.frames, world, ks[0]->half_len);
-		status(std::format("  {} taps, {} sample blocks of up to {} frames, halo {} frames each side",
-		                   fir_gpu_kernel_num_taps(ks[0]->k), world, blocks[0].frames, ks[0]->half_len));
+		status(std::format("  {} taps{}", fir_gpu_kernel_num_taps(ks[0]->k),
+		                   world > 1 ? std::format(", {} sample blocks of up to {} frames, halo {} frames each side", world,
+		                                           blocks[0].frames, ks[0]->half_len)
+		                             : std::string()));
 		status("Filtering.");
+		Progress bar;
+		bar.total = (int64_t) l.frames;
+		bar.tty = ::isatty(1) != 0;
 		std::vector<double> peaks(world, 0.0);
 		std::vector<std::exception_ptr> errs(world);
 		std::atomic<bool> failed{false};
-		std::barrier sync((std::ptrdiff_t) world);
+		std::barrier sync((std::ptrdiff_t) world + 1);
 		std::vector<std::thread> th;
 		for (size_t r = 0; r < world; ++r)
 			th.emplace_back([&, r] {
 				const Block& b = blocks[r];
 				try {
-					if (b.frames) {
-						const fir_gpu_pcm fmt = make_fmt(l, b.frames, b.halo_l, b.halo_r);
-						check(fir_gpu_apply(ctxs[r], ks[r]->k, pcm.p + (uint64_t) (b.start - b.halo_l) * fb, &fmt),
-						      "fir_gpu_apply");
-						check(fir_gpu_peak(ctxs[r], &peaks[r]), "fir_gpu_peak");
-					}
+					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
 				}
-				// every upload is complete and every peak known beyond this point:
-				// the blocks may now be overwritten in place with the common scale
+				sync.arrive_and_wait(); // every peak is known: main decides the scale, creates the output
 				sync.arrive_and_wait();
 				if (failed || !b.frames) return;
 				try {
-					const double pk = *std::max_element(peaks.begin(), peaks.end());
-					check(fir_gpu_encode(ctxs[r], scale_for_peak(pk, opts.normalize), pcm.p + (uint64_t) b.start * fb),
-					      "fir_gpu_encode");
+					encode_block(ctxs[r], l, b, scale, out_fd);
 				} catch (...) {
 					errs[r] = std::current_exception();
+					failed = true;
 				}
 			});
+		sync.arrive_and_wait();
+		try {
+			if (!failed) {
+				peak = *std::max_element(peaks.begin(), peaks.end());     // host max over the GPUs' peaks
+				scale = scale_for_peak(peak, opts.normalize);             // ProcessFile.cp:98-101
+				if (scale != 1.0) status("Doing audio normalize.");
+				status("Writing output file.");
+				out_fd = in.create_output(output_path);                   // every non-sample byte, verbatim
+			}
+		} catch (...) {
+			errs.push_back(std::current_exception());
+			failed = true;
+		}
+		sync.arrive_and_wait();
 		for (auto& t : th) t.join();
+		if (out_fd >= 0) AudioContainer::close_output(out_fd);
 		for (auto& e : errs)
 			if (e) std::rethrow_exception(e);
-		peak = *std::max_element(peaks.begin(), peaks.end());
-		scale = scale_for_peak(peak, opts.normalize);
-		if (scale != 1.0) status("Doing audio normalize.");
 		for (size_t r = 0; r < world; ++r) status(std::format("  GPU {}:{}", r, timing_line(ctxs[r])));
+	} else {
+		status("Writing output file.");
+		AudioContainer::close_output(in.create_output(output_path));
 	}
 	status(std::format("  peak {:.9f}, scale {:.9f}", peak, scale));
-
-	status("Writing output file.");                                  // ProcessFile.cp:104-117
-	const int fd = in.create_output(output_path);                    // every non-sample byte, verbatim
-	try {
-		AudioContainer::write_payload(fd, l, 0, l.payload_bytes, pcm.p);
-	} catch (...) {
-		AudioContainer::close_output(fd);
-		throw;
-	}
-	AudioContainer::close_output(fd);
 	status("");
 }
 

@@ -126,6 +126,24 @@ FIR_GPU_API void fir_gpu_kernel_free(fir_gpu_kernel *k);
 FIR_GPU_API int fir_gpu_apply(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const void *pcm_host,
                               const fir_gpu_pcm *fmt);
 
+/* Streamed filter phase: the same work as fir_gpu_apply with the payload arriving
+ * piece by piece, so that file reads overlap the upload and the FIR (the reference
+ * reads the whole file first, ProcessFile.cp:41).  begin announces the layout; each
+ * feed hands over the NEXT `bytes` of the buffer fir_gpu_apply would have received
+ * (any split, in order) and starts every chunk whose samples have landed; end starts
+ * the rest and parks the signal.  When feed(n) returns, the host buffer given to
+ * feed(n-1) is free again (alternate two buffers); after end all are. */
+FIR_GPU_API int fir_gpu_apply_begin(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const fir_gpu_pcm *fmt);
+FIR_GPU_API int fir_gpu_apply_feed(fir_gpu_ctx *ctx, const void *pcm_host, size_t bytes);
+FIR_GPU_API int fir_gpu_apply_end(fir_gpu_ctx *ctx);
+
+/* Progress hook (the reference reports progress from apply_filter_range,
+ * FilterCore.h:38-54, ProgressBar.h:58-82): fn(done_frames, total_frames, user) is
+ * called as each chunk of the FIR COMPLETES on the device, from a CUDA callback
+ * thread -- it must not call into this library or CUDA.  NULL removes it. */
+typedef void (*fir_gpu_progress_fn)(int64_t done_frames, int64_t total_frames, void *user);
+FIR_GPU_API int fir_gpu_set_progress(fir_gpu_ctx *ctx, fir_gpu_progress_fn fn, void *user);
+
 /* Same with the PCM already resident in device memory (no H2D). */
 FIR_GPU_API int fir_gpu_apply_dev(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const void *pcm_dev,
                                   const fir_gpu_pcm *fmt);
@@ -163,6 +181,10 @@ FIR_GPU_API int fir_gpu_peak_recompute(fir_gpu_ctx *ctx, double *peak);
  * the signed range, no dither), interleave, endian as in the matching apply;
  * writes frames*channels*bits/8 bytes to pcm_host.  Synchronous on return. */
 FIR_GPU_API int fir_gpu_encode(fir_gpu_ctx *ctx, double scale, void *pcm_host);
+/* Frames [first_frame, first_frame + frames) only, into pcm_host (that many frames):
+ * lets the host write the output file piece by piece while the next piece encodes. */
+FIR_GPU_API int fir_gpu_encode_range(fir_gpu_ctx *ctx, double scale, int64_t first_frame, int64_t frames,
+                                     void *pcm_host);
 /* Same into device memory, asynchronous. */
 FIR_GPU_API int fir_gpu_encode_dev(fir_gpu_ctx *ctx, double scale, void *pcm_dev);
 

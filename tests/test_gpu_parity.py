@@ -421,3 +421,52 @@ def test_halo_semantics_missing_halo_is_zero_extra_halo_is_ignored(ctx, oracle_m
             scale = oracle_mod.fir_abs_scale(xx, taps, s, e)[s:e]
             assert np.all(np.abs(y[c] - want) <= TOL * scale + 1e-300), (hl, hr)
     k.free()
+
+
+def test_streamed_apply_progress_and_ranged_encode_are_bit_exact(ctx, oracle_mod):
+    """fir_gpu_apply_begin/_feed/_end with the payload split at arbitrary byte positions ==
+    fir_gpu_apply; the progress hook reports every chunk; fir_gpu_encode_range pieces ==
+    fir_gpu_encode."""
+    from audio_fir_filter_b200 import capi
+
+    fs, ch, bits, be = 8000, 3, 24, True
+    frames, hl, hr = 200_000, 100, 320
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)
+    pcm = oracle_mod.synth_pcm(8, 0, hl + frames + hr, ch, bits, be, fs)
+    ctx.apply(k, pcm, frames, ch, bits, be, hl, hr)
+    y0, p0 = ctx.parked(frames, ch), ctx.peak()
+    whole = np.empty(frames * ch * bits // 8, dtype=np.uint8)
+    ctx.encode(0.9, whole)
+
+    cuts = [0, 1, 7, 4096, 4099, 300_001, 300_001, 1_000_000, pcm.size]      # odd sizes, an empty piece
+    pieces = [pcm[a:b].copy() for a, b in zip(cuts[:-1], cuts[1:])]
+    seen = []
+    ctx.set_progress(lambda d, t: seen.append((d, t)))
+    try:
+        ctx.apply_streamed(k, pieces, frames, ch, bits, be, hl, hr)
+        assert ctx.peak() == p0
+    finally:
+        ctx.set_progress(None)
+    assert np.array_equal(ctx.parked(frames, ch), y0)
+    assert len(seen) >= 2 and seen[-1] == (frames, frames)
+    assert all(a[0] < b[0] for a, b in zip(seen[:-1], seen[1:]))
+
+    fb = ch * bits // 8
+    out = np.zeros_like(whole)
+    for f0 in range(0, frames, 65_536):
+        n = min(65_536, frames - f0)
+        ctx.encode_range(0.9, f0, n, out[f0 * fb:(f0 + n) * fb])
+    assert np.array_equal(out, whole)
+
+    # protocol errors
+    fmt = ctx._fmt(1000, ch, bits, be)
+    import ctypes as C
+    L = capi.lib()
+    assert L.fir_gpu_apply_feed(ctx._h, pcm.ctypes.data, 10) == capi.ERR_STATE          # nothing open
+    assert L.fir_gpu_apply_begin(ctx._h, k._h, C.byref(fmt)) == capi.OK
+    assert L.fir_gpu_apply_feed(ctx._h, pcm.ctypes.data, 1000 * fb + 1) == capi.ERR_INVALID   # too many bytes
+    assert L.fir_gpu_apply_feed(ctx._h, pcm.ctypes.data, 500 * fb) == capi.OK
+    assert L.fir_gpu_apply_end(ctx._h) == capi.ERR_STATE                                 # bytes missing
+    with pytest.raises(capi.FirGpuError):
+        ctx.encode_range(1.0, 1, 10, out)                                               # odd first frame
+    k.free()
