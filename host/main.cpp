@@ -45,7 +45,7 @@ int main(int argc, char** argv)
 			if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
 			GpuPool pool(cli.gpus);
 			// main.cp:69-72 prints its resource line only when -v is NOT given; kept as is
-			if (!opts.verbose) std::cout << std::format("Using {} GPU(s).", pool.size()) << std::endl;
+			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
 			if (fs::exists(out)) fs::remove(out);
 			process_file(in, out, opts, pool);
 		} else {
@@ -72,7 +72,7 @@ int main(int argc, char** argv)
 				jobs.emplace_back(in, out);
 			}
 			GpuPool pool(cli.gpus);
-			if (!opts.verbose) std::cout << std::format("Using {} GPU(s).", pool.size()) << std::endl;
+			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
 			for (const auto& j : jobs)
 				if (fs::exists(j.second)) fs::remove(j.second);
 			process_batch(jobs, opts, pool);

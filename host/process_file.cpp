@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <barrier>
+#include <chrono>
+#include <cmath>
 #include <exception>
 #include <format>
 #include <iostream>
@@ -30,18 +32,6 @@ void check(int rc, const char* what)
 {
 	if (rc != FIR_GPU_OK) throw GpuError(rc, std::format("{}: {}", what, fir_gpu_last_error()));
 }
-
-struct PinnedBytes {
-	unsigned char* p = nullptr;
-	explicit PinnedBytes(size_t n)
-	{
-		p = static_cast<unsigned char*>(fir_gpu_host_alloc(n ? n : 1));
-		if (!p) throw GpuError(FIR_GPU_ERR_NOMEM, std::format("pinned host buffer of {} bytes: {}", n, fir_gpu_last_error()));
-	}
-	~PinnedBytes() { fir_gpu_host_free(p); }
-	PinnedBytes(const PinnedBytes&) = delete;
-	PinnedBytes& operator=(const PinnedBytes&) = delete;
-};
 
 struct KernelHandle {
 	fir_gpu_kernel* k = nullptr;
@@ -129,7 +119,7 @@ constexpr uint64_t PIECE_BYTES = 64ull << 20; // file <-> pinned buffer <-> devi
 
 // One sample block of the file on one GPU, streamed: file reads overlap upload and FIR.
 void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContainer& in, const Block& b, double* peak,
-                  Progress* bar)
+                  Progress* bar, GpuPool& pool, size_t slot)
 {
 	const PcmLayout& l = in.pcm();
 	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
@@ -138,8 +128,8 @@ void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContaine
 	check(fir_gpu_set_progress(ctx, on_chunk_done, &bp), "fir_gpu_set_progress");
 	check(fir_gpu_apply_begin(ctx, k, &fmt), "fir_gpu_apply_begin");
 	const uint64_t first = (uint64_t) (b.start - b.halo_l) * fb, total = (uint64_t) (b.halo_l + b.frames + b.halo_r) * fb;
-	PinnedBytes buf0(std::min(total, PIECE_BYTES)), buf1(std::min(total, PIECE_BYTES));
-	unsigned char* bufs[2] = {buf0.p, buf1.p};
+	unsigned char* bufs[2] = {pool.staging(slot, 0, std::min(total, PIECE_BYTES)),
+	                          pool.staging(slot, 1, std::min(total, PIECE_BYTES))};
 	int i = 0;
 	for (uint64_t off = 0; off < total; off += PIECE_BYTES, i ^= 1) {
 		const uint64_t n = std::min(PIECE_BYTES, total - off);
@@ -153,12 +143,13 @@ void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContaine
 
 // Encode the block with the common scale and write it into the output's sample chunk,
 // piece by piece: the file write of one piece overlaps the encode + download of the next.
-void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double scale, int out_fd)
+void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double scale, int out_fd, GpuPool& pool,
+                  size_t slot)
 {
 	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
 	const int64_t piece = std::max<int64_t>(2, (int64_t) (PIECE_BYTES / fb) & ~(int64_t) 1);
-	PinnedBytes buf0((uint64_t) std::min(piece, b.frames) * fb), buf1((uint64_t) std::min(piece, b.frames) * fb);
-	unsigned char* bufs[2] = {buf0.p, buf1.p};
+	unsigned char* bufs[2] = {pool.staging(slot, 2, (uint64_t) std::min(piece, b.frames) * fb),
+	                          pool.staging(slot, 3, (uint64_t) std::min(piece, b.frames) * fb)};
 	std::thread writer;
 	std::exception_ptr werr;
 	int i = 0;
@@ -179,9 +170,11 @@ void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double s
 	if (werr) std::rethrow_exception(werr);
 }
 
+// ctxs[r] lives in pool slot first_slot + r (its pinned staging buffers are taken from there).
 void run_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
-              const FilterOptions& opts, const std::vector<fir_gpu_ctx*>& ctxs)
+              const FilterOptions& opts, GpuPool& pool, const std::vector<fir_gpu_ctx*>& ctxs, size_t first_slot)
 {
+	const auto t_start = std::chrono::steady_clock::now();
 	auto status = [&](const std::string& s) {
 		if (opts.verbose) say(s);
 	};
@@ -226,7 +219,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 			th.emplace_back([&, r] {
 				const Block& b = blocks[r];
 				try {
-					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar);
+					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar, pool, first_slot + r);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
@@ -235,7 +228,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				sync.arrive_and_wait();
 				if (failed || !b.frames) return;
 				try {
-					encode_block(ctxs[r], l, b, scale, out_fd);
+					encode_block(ctxs[r], l, b, scale, out_fd, pool, first_slot + r);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
@@ -264,7 +257,8 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		status("Writing output file.");
 		AudioContainer::close_output(in.create_output(output_path));
 	}
-	status(std::format("  peak {:.9f}, scale {:.9f}", peak, scale));
+	status(std::format("  peak {:.9f}, scale {:.9f}, {:.3f} s", peak, scale,
+	                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count()));
 	status("");
 }
 
@@ -280,36 +274,97 @@ GpuPool::GpuPool(unsigned want)
 	const int n = fir_gpu_device_count();
 	if (n <= 0)
 		throw GpuError(FIR_GPU_ERR_NO_DEVICE, "no usable B200 (sm_100) device; lowcut has no CPU path");
+	forced_ = want != 0;
 	const int use = want == 0 ? n : std::min<int>((int) want, n);
-	// device_count() counts usable devices; walk the ordinals until `use` contexts exist
-	for (int d = 0; (int) ctx_.size() < use && d < 64; ++d) {
-		fir_gpu_ctx* c = nullptr;
-		const int rc = fir_gpu_create(d, &c);
-		if (rc == FIR_GPU_OK) ctx_.push_back(c);
-		else if (rc == FIR_GPU_ERR_INVALID) break; // past the last ordinal
-	}
-	if (ctx_.empty()) throw GpuError(FIR_GPU_ERR_NO_DEVICE, std::string("cannot create a GPU context: ") + fir_gpu_last_error());
+	for (int d = 0; d < use; ++d) ordinals_.push_back(d); // contexts skip non-sm_100 ordinals themselves
+	lanes_.resize(ordinals_.size());
 }
 
 GpuPool::~GpuPool()
 {
-	for (fir_gpu_ctx* c : ctx_) fir_gpu_destroy(c);
+	for (Lane& l : lanes_) {
+		for (unsigned char* b : l.buf) fir_gpu_host_free(b);
+		fir_gpu_destroy(l.ctx);
+	}
+}
+
+std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n)
+{
+	n = std::max<size_t>(1, std::min(n, lanes_.size()));
+	std::vector<std::thread> th;
+	std::vector<std::string> errs(n);
+	for (size_t i = 0; i < n; ++i)
+		if (!lanes_[i].ctx)
+			th.emplace_back([this, i, &errs] {
+				// usable devices may not be the first ordinals: walk until one opens
+				for (int d = ordinals_[i]; d < 64; d += (int) ordinals_.size()) {
+					const int rc = fir_gpu_create(d, &lanes_[i].ctx);
+					if (rc == FIR_GPU_OK) return;
+					errs[i] = fir_gpu_last_error();
+					if (rc != FIR_GPU_ERR_NO_DEVICE) return;
+				}
+			});
+	for (auto& t : th) t.join();
+	std::vector<fir_gpu_ctx*> out;
+	for (size_t i = 0; i < n; ++i) {
+		if (!lanes_[i].ctx) throw GpuError(FIR_GPU_ERR_NO_DEVICE, "cannot create a GPU context: " + errs[i]);
+		out.push_back(lanes_[i].ctx);
+	}
+	return out;
+}
+
+unsigned char* GpuPool::staging(size_t slot, int which, size_t bytes)
+{
+	Lane& l = lanes_.at(slot);
+	if (l.cap[which] < bytes) {
+		fir_gpu_host_free(l.buf[which]);
+		l.buf[which] = static_cast<unsigned char*>(fir_gpu_host_alloc(bytes));
+		l.cap[which] = l.buf[which] ? bytes : 0;
+		if (!l.buf[which])
+			throw GpuError(FIR_GPU_ERR_NOMEM, std::format("pinned host buffer of {} bytes: {}", bytes, fir_gpu_last_error()));
+	}
+	return l.buf[which];
+}
+
+// Seconds of FIR one B200 needs for this much work (35 TFLOP/s measured), used to
+// decide how many GPUs are worth starting.
+static double fir_seconds(double taps, double frames, double channels)
+{
+	return 2.0 * taps * frames * channels / 35.0e12;
+}
+
+static double estimate_file_seconds(const std::filesystem::path& p, const FilterOptions& opts)
+{
+	AudioContainer in(p);
+	const PcmLayout& l = in.pcm();
+	if (!(l.sample_rate > 0.0) || !(opts.slope > 0.0)) return 0.0;
+	return fir_seconds(4.0 * l.sample_rate / opts.slope + 1.0, (double) l.frames, l.channels);
+}
+
+static size_t gpus_worth_starting(const GpuPool& pool, double seconds)
+{
+	if (pool.forced()) return pool.limit();
+	// every extra GPU should bring at least ~0.2 s of FIR with it (context start-up is of that order)
+	const double g = std::floor(seconds / 0.2);
+	return (size_t) std::clamp<double>(g, 1.0, (double) pool.limit());
 }
 
 void process_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
                   const FilterOptions& opts, GpuPool& pool)
 {
-	std::vector<fir_gpu_ctx*> ctxs;
-	for (size_t i = 0; i < pool.size(); ++i) ctxs.push_back(pool.ctx(i));
-	run_file(input_path, output_path, opts, ctxs);
+	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
+	run_file(input_path, output_path, opts, pool, pool.acquire(world), 0);
 }
 
 void process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
                    const FilterOptions& opts, GpuPool& pool)
 {
-	const size_t workers = std::min(pool.size(), jobs.size());
+	double seconds = 0.0;
+	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
+	const size_t workers = std::min(gpus_worth_starting(pool, seconds), jobs.size());
+	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(workers);
 	if (workers <= 1) {
-		for (const auto& j : jobs) run_file(j.first, j.second, opts, {pool.ctx(0)});
+		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, 0);
 		return;
 	}
 	std::atomic<size_t> next{0};
@@ -320,7 +375,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 		th.emplace_back([&, w] {
 			try {
 				for (size_t i = next++; i < jobs.size() && !failed; i = next++)
-					run_file(jobs[i].first, jobs[i].second, opts, {pool.ctx(w)});
+					run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, w);
 			} catch (...) {
 				errs[w] = std::current_exception();
 				failed = true;

@@ -21,19 +21,32 @@ struct FilterOptions {
 	unsigned num_threads = 0; // -t: accepted, unused (the device grid replaces the thread fan-out)
 };
 
-// One fir_gpu context per B200 in use.  Throws GpuError if there is none: this
-// program has no CPU path.
+// The B200s this run may use, one fir_gpu context (and one set of pinned staging
+// buffers) per device, created on first use: starting a CUDA context costs far more
+// than filtering a short file, so a GPU is only brought up when there is work for it.
+// Throws GpuError if there is no usable device: this program has no CPU path.
 class GpuPool {
 public:
-	explicit GpuPool(unsigned want /* 0 = all usable devices */);
+	explicit GpuPool(unsigned want /* 0 = choose by the amount of work, up to every usable device */);
 	~GpuPool();
 	GpuPool(const GpuPool&) = delete;
 	GpuPool& operator=(const GpuPool&) = delete;
-	size_t size() const { return ctx_.size(); }
-	fir_gpu_ctx* ctx(size_t i) const { return ctx_[i]; }
+	size_t limit() const { return ordinals_.size(); } // devices that may be used
+	bool forced() const { return forced_; }             // -g N given: use exactly that many when possible
+	// Contexts 0..n-1, created in parallel if they do not exist yet.
+	std::vector<fir_gpu_ctx*> acquire(size_t n);
+	// Two pinned buffers of `bytes` for upload and two for download, per device, reused across files.
+	unsigned char* staging(size_t device_slot, int which /*0..3*/, size_t bytes);
 
 private:
-	std::vector<fir_gpu_ctx*> ctx_;
+	struct Lane {
+		fir_gpu_ctx* ctx = nullptr;
+		unsigned char* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+		size_t cap[4] = {0, 0, 0, 0};
+	};
+	std::vector<int> ordinals_;
+	std::vector<Lane> lanes_;
+	bool forced_ = false;
 };
 
 // One file (ProcessFile.cp:27-120).  A file long enough is split into contiguous
