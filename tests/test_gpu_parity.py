@@ -470,3 +470,60 @@ def test_streamed_apply_progress_and_ranged_encode_are_bit_exact(ctx, oracle_mod
     with pytest.raises(capi.FirGpuError):
         ctx.encode_range(1.0, 1, 10, out)                                               # odd first frame
     k.free()
+
+
+@pytest.mark.parametrize("bits,be,ch,frames,shift", [
+    (24, False, 7, 1, 0), (24, True, 7, 2, 1), (16, False, 1, 3, 1), (32, True, 5, 17, 3), (24, False, 1, 33, 2),
+    (16, True, 6, 4097, 1), (24, False, 2, 1365, 3), (32, False, 256, 40, 0), (24, True, 3, 70_001, 5),
+])
+def test_ragged_and_misaligned_payloads(ctx, oracle_mod, bits, be, ch, frames, shift):
+    """Tiny files (shorter than the kernel: the reference's UB region, here the zero-padded
+    formula), odd frame sizes, and payloads that start at any byte address -- the codec
+    kernels' ragged head/tail paths must not touch a byte outside the payload."""
+    import torch
+
+    fs = 8000
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)                 # 641 taps
+    n = frames * ch * bits // 8
+    pcm = oracle_mod.synth_pcm(frames + ch, 0, frames, ch, bits, be, fs)
+    want = oracle_mod.process(pcm, frames, ch, bits, be, 40.0 / fs, 50.0 / fs, True)
+    # host path, misaligned host pointer
+    hbuf = np.zeros(n + 64, dtype=np.uint8)
+    hbuf[shift:shift + n] = pcm
+    ctx.apply(k, hbuf[shift:shift + n], frames, ch, bits, be)
+    y = ctx.parked(frames, ch)
+    assert np.max(np.abs(y - want["y"])) <= 1e-12 * max(np.abs(want["y"]).max(), 1e-30)
+    pk = ctx.peak()
+    out = np.full(n + 64, 0xA5, dtype=np.uint8)
+    ctx.encode(1.0 / pk, out[shift:shift + n])
+    assert np.all(out[:shift] == 0xA5) and np.all(out[shift + n:] == 0xA5)      # guard bytes untouched
+    nflip, mx = lsb_flips(out[shift:shift + n], want["pcm"], bits, be)
+    assert mx <= 1 and nflip <= 2
+    # device path, misaligned device pointers for both input and output
+    d_in = torch.zeros(n + 64, dtype=torch.uint8, device="cuda:0")
+    d_in[shift:shift + n] = torch.from_numpy(pcm).cuda()
+    d_out = torch.full((n + 64,), 0xA5, dtype=torch.uint8, device="cuda:0")
+    ctx.apply_dev(k, d_in.data_ptr() + shift, frames, ch, bits, be)
+    assert ctx.peak() == pk
+    ctx.encode_dev(1.0 / pk, d_out.data_ptr() + shift)
+    ctx.synchronize()
+    o = d_out.cpu().numpy()
+    assert np.array_equal(o[shift:shift + n], out[shift:shift + n])
+    assert np.all(o[:shift] == 0xA5) and np.all(o[shift + n:] == 0xA5)
+    k.free()
+
+
+def test_reference_make_test_settings_whole_path(ctx, oracle_mod):
+    """`lowcut -f 440 -s 80 -n` -- the settings of the reference's own `make test`
+    (Makefile:47) -- on a 44.1 kHz stereo 16-bit file: odd 4/bw (2205 -> M = 2206)."""
+    from audio_fir_filter_b200 import FilterOptions, PcmInfo, process_pcm
+
+    fs, ch, bits, frames = 44100, 2, 16, 150_000
+    pcm = oracle_mod.synth_pcm(440, 0, frames, ch, bits, False, fs, gain=1.1)
+    out = np.empty_like(pcm)
+    r = process_pcm(ctx, pcm, PcmInfo(frames, ch, bits, False, float(fs)), FilterOptions(440.0, 80.0, True), out)
+    assert r["taps"] == 2207
+    want = oracle_mod.process(pcm, frames, ch, bits, False, 440.0 / fs, 80.0 / fs, True)
+    assert abs(r["peak"] - want["peak"]) <= 1e-12 * want["peak"]
+    nflip, mx = lsb_flips(out, want["pcm"], bits, False)
+    assert mx <= 1 and nflip <= 2
