@@ -170,9 +170,10 @@ void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double s
 	if (werr) std::rethrow_exception(werr);
 }
 
-// ctxs[r] lives in pool slot first_slot + r (its pinned staging buffers are taken from there).
+// ctxs[r] lives in pool slot slots[r] (its pinned staging buffers are taken from there).
 void run_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
-              const FilterOptions& opts, GpuPool& pool, const std::vector<fir_gpu_ctx*>& ctxs, size_t first_slot)
+              const FilterOptions& opts, GpuPool& pool, const std::vector<fir_gpu_ctx*>& ctxs,
+              const std::vector<size_t>& slots)
 {
 	const auto t_start = std::chrono::steady_clock::now();
 	auto status = [&](const std::string& s) {
@@ -219,7 +220,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 			th.emplace_back([&, r] {
 				const Block& b = blocks[r];
 				try {
-					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar, pool, first_slot + r);
+					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar, pool, slots[r]);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
@@ -228,7 +229,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				sync.arrive_and_wait();
 				if (failed || !b.frames) return;
 				try {
-					encode_block(ctxs[r], l, b, scale, out_fd, pool, first_slot + r);
+					encode_block(ctxs[r], l, b, scale, out_fd, pool, slots[r]);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
@@ -276,8 +277,8 @@ GpuPool::GpuPool(unsigned want)
 		throw GpuError(FIR_GPU_ERR_NO_DEVICE, "no usable B200 (sm_100) device; lowcut has no CPU path");
 	forced_ = want != 0;
 	const int use = want == 0 ? n : std::min<int>((int) want, n);
-	for (int d = 0; d < use; ++d) ordinals_.push_back(d); // contexts skip non-sm_100 ordinals themselves
-	lanes_.resize(ordinals_.size());
+	for (int d = 0; d < use; ++d) ordinals_.push_back(d);
+	lanes_.resize(2 * ordinals_.size());
 }
 
 GpuPool::~GpuPool()
@@ -288,28 +289,26 @@ GpuPool::~GpuPool()
 	}
 }
 
-std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n)
+std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, bool both_subs, std::vector<size_t>* slots)
 {
-	n = std::max<size_t>(1, std::min(n, lanes_.size()));
+	n_devices = std::max<size_t>(1, std::min(n_devices, ordinals_.size()));
+	std::vector<size_t> want;
+	for (size_t sub = 0; sub < (both_subs ? 2u : 1u); ++sub)
+		for (size_t d = 0; d < n_devices; ++d) want.push_back(2 * d + sub);
 	std::vector<std::thread> th;
-	std::vector<std::string> errs(n);
-	for (size_t i = 0; i < n; ++i)
-		if (!lanes_[i].ctx)
-			th.emplace_back([this, i, &errs] {
-				// usable devices may not be the first ordinals: walk until one opens
-				for (int d = ordinals_[i]; d < 64; d += (int) ordinals_.size()) {
-					const int rc = fir_gpu_create(d, &lanes_[i].ctx);
-					if (rc == FIR_GPU_OK) return;
-					errs[i] = fir_gpu_last_error();
-					if (rc != FIR_GPU_ERR_NO_DEVICE) return;
-				}
+	std::vector<std::string> errs(lanes_.size());
+	for (size_t slot : want)
+		if (!lanes_[slot].ctx)
+			th.emplace_back([this, slot, &errs] {
+				if (fir_gpu_create(ordinals_[slot / 2], &lanes_[slot].ctx) != FIR_GPU_OK) errs[slot] = fir_gpu_last_error();
 			});
 	for (auto& t : th) t.join();
 	std::vector<fir_gpu_ctx*> out;
-	for (size_t i = 0; i < n; ++i) {
-		if (!lanes_[i].ctx) throw GpuError(FIR_GPU_ERR_NO_DEVICE, "cannot create a GPU context: " + errs[i]);
-		out.push_back(lanes_[i].ctx);
+	for (size_t slot : want) {
+		if (!lanes_[slot].ctx) throw GpuError(FIR_GPU_ERR_NO_DEVICE, "cannot create a GPU context: " + errs[slot]);
+		out.push_back(lanes_[slot].ctx);
 	}
+	if (slots) *slots = want;
 	return out;
 }
 
@@ -353,7 +352,9 @@ void process_file(const std::filesystem::path& input_path, const std::filesystem
                   const FilterOptions& opts, GpuPool& pool)
 {
 	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
-	run_file(input_path, output_path, opts, pool, pool.acquire(world), 0);
+	std::vector<size_t> slots;
+	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, false, &slots);
+	run_file(input_path, output_path, opts, pool, ctxs, slots);
 }
 
 void process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
@@ -361,10 +362,13 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 {
 	double seconds = 0.0;
 	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
-	const size_t workers = std::min(gpus_worth_starting(pool, seconds), jobs.size());
-	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(workers);
+	const size_t gpus = std::min(gpus_worth_starting(pool, seconds), jobs.size());
+	// two lanes per GPU: while one file filters, the other reads, uploads, downloads, writes
+	std::vector<size_t> slots;
+	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(gpus, jobs.size() > gpus, &slots);
+	const size_t workers = std::min(ctxs.size(), jobs.size());
 	if (workers <= 1) {
-		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, 0);
+		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, {slots[0]});
 		return;
 	}
 	std::atomic<size_t> next{0};
@@ -375,7 +379,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 		th.emplace_back([&, w] {
 			try {
 				for (size_t i = next++; i < jobs.size() && !failed; i = next++)
-					run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, w);
+					run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, {slots[w]});
 			} catch (...) {
 				errs[w] = std::current_exception();
 				failed = true;

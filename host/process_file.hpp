@@ -33,10 +33,12 @@ public:
 	GpuPool& operator=(const GpuPool&) = delete;
 	size_t limit() const { return ordinals_.size(); } // devices that may be used
 	bool forced() const { return forced_; }             // -g N given: use exactly that many when possible
-	// Contexts 0..n-1, created in parallel if they do not exist yet.
-	std::vector<fir_gpu_ctx*> acquire(size_t n);
-	// Two pinned buffers of `bytes` for upload and two for download, per device, reused across files.
-	unsigned char* staging(size_t device_slot, int which /*0..3*/, size_t bytes);
+	// Lanes: two contexts per device (slot = 2*device + sub).  Block mode uses sub 0 of
+	// the first n devices; batch mode both subs, so that one file's I/O, upload and
+	// download overlap the other's FIR on the same GPU.  Created in parallel on demand.
+	std::vector<fir_gpu_ctx*> acquire(size_t n_devices, bool both_subs, std::vector<size_t>* slots = nullptr);
+	// Two pinned buffers of `bytes` for upload and two for download, per lane, reused across files.
+	unsigned char* staging(size_t slot, int which /*0..3*/, size_t bytes);
 
 private:
 	struct Lane {

@@ -35,12 +35,13 @@ with tempfile.TemporaryDirectory(dir="/tmp") as d:
     print(f"cfg4 file ({len(pcm) / 1e6:.0f} MB, 9601 taps): {dt:.3f} s wall")
     print("\n".join(l for l in out.splitlines() if "device time" in l or "peak" in l))
     files = []
-    for i in range(8):
+    NB = int(os.environ.get("BATCH", "32"))
+    for i in range(NB):
         p = os.path.join(d, f"b{i}.wav")
         os.link(w, p)
         files.append(p)
     dt, _ = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"))
-    print(f"batch of 8 such files: {dt:.3f} s wall ({8 * 28.8 / dt:.0f} MSamples/s incl. file I/O)")
+    print(f"batch of {NB} such files: {dt:.3f} s wall ({NB * 28.8 / dt:.0f} MSamples/s incl. file I/O and start-up)")
     pcm = oracle.synth_pcm(2, 0, 26_460_000, 2, 16, True, 44100).tobytes()
     a = os.path.join(d, "cfg2.aif")
     open(a, "wb").write(aiff_bytes(pcm, 2, 16, 44100.0))
