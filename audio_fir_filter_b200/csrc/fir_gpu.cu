@@ -569,9 +569,9 @@ int fir_gpu_build_kernel(fir_gpu_ctx* c, double fc_norm, double bw_norm, fir_gpu
 	int rc = alloc_kernel(c, M + 1, &k);
 	if (rc) return rc;
 	const int blocks = (int) ((M + 1 + 255) / 256);
-	double* d_lp = nullptr;
+	dd* d_lp = nullptr;
 	dd* d_part = nullptr;
-	cudaError_t e = cudaMalloc(&d_lp, (size_t) (M + 1) * sizeof(double));
+	cudaError_t e = cudaMalloc(&d_lp, (size_t) (M + 1) * sizeof(dd));
 	if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t) (blocks + 1) * sizeof(dd));
 	if (e != cudaSuccess) {
 		cudaFree(d_lp);

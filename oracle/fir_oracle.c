@@ -18,8 +18,10 @@
  * S. W. Smith, "The Scientist and Engineer's Guide to DSP", ch. 16), with the
  * decisions D1..D5 listed in DESIGN.md.
  *
- * Precision: tap generation and normalisation in x87 80-bit long double, rounded
- * once to binary64 (north_star: "normalised in extended precision").  The "hi"
+ * Precision: tap generation and normalisation in x87 80-bit long double (exact angle
+ * reduction, cancellation-free window form), rounded once more to binary64
+ * (north_star: "normalised in extended precision"); pinned against 50-digit mpmath
+ * values in tests/golden/taps_*.npz to <= 1 ulp.  The "hi"
  * FIR keeps FP64 samples and accumulates in long double, so its result is the
  * correctly rounded sum to within ~1e-19 relative of sum|h*x|.
  *
@@ -97,7 +99,7 @@ ORACLE_API int64_t oracle_kernel_order(double bw_norm)
 /* WindowedSinc<float64_t>(fc, bw) followed by makeLowCut()
  * (call sites ProcessFile.cp:48-50; body absent, restated from Smith ch.16):
  *   low-pass   h[i] = sin(2 pi fc (i-M/2)) / (i-M/2)   (2 pi fc at the centre)
- *              h[i] *= 0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M)
+ *              h[i] *= 0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M)   (Blackman)
  *              h   /= sum(h)                       (unity gain at DC)
  *   low-cut    h = -h ; h[M/2] += 1                (spectral inversion)
  * All in long double; taps[0..M] receive the values rounded to binary64.
@@ -119,9 +121,30 @@ ORACLE_API int oracle_build_lowcut(double fc_norm, double bw_norm, double *taps,
 	 * centre, mirror the rest, so the symmetry holds bit for bit. */
 	for (int64_t i = 0; i <= H; ++i) {
 		const long double m = (long double)(i - H);
-		long double s = (i == H) ? w : sinl(w * m) / m;
-		const long double a = 2.0L * PI_L * (long double) i / (long double) M;
-		const long double win = 0.42L - 0.5L * cosl(a) + 0.08L * cosl(2.0L * a);
+		long double s;
+		if (i == H) {
+			s = w;
+		} else {
+			/* sin(2 pi fc m) with the angle reduced exactly: p = 2 fc m half-turns
+			 * as an unevaluated sum p_hi + p_lo (fmal keeps the remainder of the
+			 * product), minus the nearest integer, then sin(pi r) * (-1)^k.  A plain
+			 * sinl(w*m) loses ~|w*m| * 2^-64 in the argument, which is a large
+			 * RELATIVE error for the taps next to the sinc's zero crossings. */
+			const long double two_fc = 2.0L * (long double) fc_norm;
+			const long double p_hi = two_fc * m;
+			const long double p_lo = fmal(two_fc, m, -p_hi);
+			const long double k = rintl(p_hi);
+			const long double r = (p_hi - k) + p_lo;
+			s = sinl(PI_L * r);
+			if (fmodl(k, 2.0L) != 0.0L) s = -s;
+			s /= m;
+		}
+		/* Blackman window 0.42 - 0.5 cos(2 pi i/M) + 0.08 cos(4 pi i/M), evaluated
+		 * in the algebraically identical form u^2 (0.36 + 0.64 u^2), u = sin(pi i/M)
+		 * (0.42 - 0.5 + 0.08 = 0): no cancellation, so the small taps at the ends
+		 * keep the full 64-bit relative accuracy. */
+		const long double u = sinl(PI_L * (long double) i / (long double) M);
+		const long double win = u * u * (0.36L + 0.64L * u * u);
 		h[i] = s * win;
 		h[M - i] = h[i];
 	}

@@ -50,7 +50,7 @@ def mp_taps(fc, bw):
 def main():
     # ---- taps ------------------------------------------------------------------
     for name, fs, f, s in [("small", 48000.0, 20.0, 200.0), ("cfg1", 48000.0, 20.0, 20.0),
-                           ("odd", 44100.0, 440.0, 80.0)]:
+                           ("odd", 44100.0, 440.0, 80.0), ("cfg2", 44100.0, 30.0, 10.0)]:
         fc, bw = f / fs, s / fs
         np.savez_compressed(os.path.join(HERE, f"taps_{name}.npz"), fc=fc, bw=bw, taps=mp_taps(fc, bw))
         print("taps", name, oracle.kernel_order(bw) + 1)

@@ -15,7 +15,7 @@ from conftest import CONFIGS, golden
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
-TAP_ULPS = 4.0   # binary64 sinpi/div/mul chain per tap + double-double normalisation
+TAP_ULPS = 1.0   # device taps (double-double, one rounding) vs the oracle's long-double taps
 
 
 def pcm_to_int(pcm, bits, be):
@@ -46,23 +46,50 @@ def test_build_kernel_matches_oracle_taps(ctx, oracle_mod, cfg):
     assert k.num_taps == c["taps"] and k.half_len == (c["taps"] - 1) // 2
     got = k.taps()
     want, ld = oracle_mod.build_lowcut(fc, bw, want_ld=True)
+    # the device carries every tap in double-double and rounds once; the oracle rounds
+    # twice (80-bit, then binary64): they differ by at most 1 ulp, on well under 1 % of the taps
     err = np.abs(got.astype(np.longdouble) - ld).astype(np.float64)
-    ulps = err / (np.spacing(np.abs(want)) + 1e-19)
-    print(f"config {cfg}: max tap error {ulps.max():.2f} ulp, {np.count_nonzero(got != want)} of {got.size} differ")
-    assert np.all(ulps <= TAP_ULPS), float(ulps.max())
+    assert np.all(err <= TAP_ULPS * np.spacing(np.abs(want))), float((err / np.spacing(np.abs(want))).max())
+    ndiff = int(np.count_nonzero(got != want))
+    print(f"config {cfg}: {ndiff} of {got.size} taps differ from the oracle's (by 1 ulp)")
+    assert ndiff <= 0.01 * got.size
     assert np.array_equal(got, got[::-1])                       # symmetric bit for bit
     assert abs(float(got.astype(np.longdouble).sum())) < 1e-15   # DC removed
+    assert got[0] == 0.0 and not np.signbit(got[0])
     k.free()
 
 
-@pytest.mark.parametrize("name", ["small", "odd"])
-def test_build_kernel_matches_mpmath_golden(ctx, name):
+@pytest.mark.parametrize("name", ["small", "odd", "cfg1", "cfg2"])
+def test_build_kernel_equals_mpmath_golden_bit_for_bit(ctx, name):
+    """The 50-digit mpmath evaluation rounded once to binary64 is the correctly rounded tap;
+    the device's double-double recipe reproduces it exactly."""
     g = golden(f"taps_{name}.npz")
     k = ctx.build_kernel(float(g["fc"]), float(g["bw"]))
     got = k.taps()
-    assert got.shape == g["taps"].shape
-    assert np.all(np.abs(got - g["taps"]) <= TAP_ULPS * (np.spacing(np.abs(g["taps"])) + 1e-19))
+    assert np.array_equal(got, g["taps"])
     k.free()
+
+
+def test_build_kernel_device_equals_host_compile_of_the_same_recipe(ctx, tmp_path):
+    """sinc_dd.cuh compiled with g++ (tests/harness) and with nvcc give the same taps for the
+    long kernels of configs 3 and 5 (no golden is stored for those: 1.5 MB each)."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = str(tmp_path / "sinc_dd_host")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", exe,
+                        os.path.join(ROOT, "tests", "harness", "sinc_dd_host.cpp"), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for cfg in (3, 5):
+        c = CONFIGS[cfg]
+        fc, bw = c["freq"] / c["fs"], c["slope"] / c["fs"]
+        k = ctx.build_kernel(fc, bw)
+        got = k.taps()
+        out = subprocess.run([exe, repr(fc), str(got.size - 1)], capture_output=True).stdout
+        assert np.array_equal(got, np.frombuffer(out, dtype=np.float64))
+        k.free()
 
 
 def test_build_kernel_rejects_bad_arguments(ctx):
