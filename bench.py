@@ -386,7 +386,7 @@ def main() -> int:
         }
     kernel.free()
 
-    if rank == 0 and not a.no_cpu and world >= 1:
+    if rank == 0 and not a.no_cpu and world == 1:   # the CPU leg is reported at N=1 only
         msps, desc, _ = cpu_reference_rate(cfg, a.cpu_seconds)
         line["cpu_baseline"] = {"value": msps, "unit": "MSamples/s", **desc}
     if world > 1:
