@@ -101,3 +101,18 @@ def test_sample_block_mode_across_gpus_equals_single_gpu(tmp_path, oracle_mod):
     r = run("-g", 2, "-v", "-f", 20, "-s", 100, "-n", src, two)
     assert r.returncode == 0 and "sample blocks" in r.stdout
     assert one.read_bytes() == two.read_bytes()
+
+
+def test_config1_full_size_file_through_the_cli(tmp_path, oracle_mod):
+    """BASELINE config 1 as a real file: 60 s stereo 48 kHz 24-bit WAVE with foreign chunks
+    either side of `data`, `lowcut -f 20 -s 20` (9601 taps): the whole payload against
+    oracle_process, every other byte against the input."""
+    fs, ch, bits, frames = 48000, 2, 24, 2_880_000
+    pcm = oracle_mod.synth_pcm(0xF1F1F1, 0, frames, ch, bits, False, fs).tobytes()
+    data = wav_bytes(pcm, ch, bits, fs)
+    src, dst = tmp_path / "cfg1.wav", tmp_path / "cfg1_out.wav"
+    src.write_bytes(data)
+    r = run("-f", 20, "-s", 20, src, dst)
+    assert r.returncode == 0, r.stderr
+    nflip = check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, False, fs, 20.0, 20.0, False)
+    print(f"config 1 through the CLI: {nflip} of {frames * ch} samples differ from the oracle by 1 LSB")

@@ -554,3 +554,38 @@ def test_reference_make_test_settings_whole_path(ctx, oracle_mod):
     assert abs(r["peak"] - want["peak"]) <= 1e-12 * want["peak"]
     nflip, mx = lsb_flips(out, want["pcm"], bits, False)
     assert mx <= 1 and nflip <= 2
+
+
+def test_repeated_passes_do_not_leak_device_memory(oracle_mod):
+    """300 apply/peak/encode passes of varying size on one context, with a progress hook and
+    two kernels alive: results stay identical and the device's free memory does not drift."""
+    import torch
+
+    from audio_fir_filter_b200 import Context
+
+    fs, ch, bits = 8000, 2, 16
+    sizes = [4000, 70_000, 12_345, 1, 33_000]
+    pcms = {n: oracle_mod.synth_pcm(n, 0, n, ch, bits, False, fs) for n in sizes}
+    with Context(0) as cx:
+        cx.set_progress(lambda d, t: None)
+        k1, k2 = cx.build_kernel(40.0 / fs, 50.0 / fs), cx.build_kernel(100.0 / fs, 400.0 / fs)
+        first = {}
+        free0 = None
+        for it in range(300):
+            n = sizes[it % len(sizes)]
+            k = k1 if it % 2 else k2
+            out = np.empty_like(pcms[n])
+            cx.apply(k, pcms[n], n, ch, bits, False)
+            pk = cx.peak()
+            cx.encode(1.0 / pk if pk > 0 else 1.0, out)
+            key = (n, it % 2)
+            if key in first:
+                assert np.array_equal(out, first[key][0]) and pk == first[key][1]
+            else:
+                first[key] = (out, pk)
+            if it == 20:
+                free0 = torch.cuda.mem_get_info(0)[0]
+        cx.set_progress(None)
+        assert abs(torch.cuda.mem_get_info(0)[0] - free0) < (64 << 20)
+        k1.free()
+        k2.free()

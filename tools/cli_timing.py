@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """GPU-box tool: wall time of the C++ host (`host/lowcut`) on real files in /tmp --
 one config-4-sized WAV (5 min stereo 48 kHz 24-bit), the config-2 AIFF, and a small batch.
-Input synthesis uses the oracle's generator (test infrastructure), the timed program is the
-product only."""
+The input PCM comes from the library's own device generator (fir_gpu_synth_pcm_dev)."""
 import os
 import subprocess
 import sys
@@ -11,8 +10,19 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-import oracle  # noqa: E402
+import torch  # noqa: E402
+
+from audio_fir_filter_b200 import capi  # noqa: E402
 from audio_fixtures import aiff_bytes, wav_bytes  # noqa: E402
+
+
+def synth(seed, frames, ch, bits, be, rate):
+    with capi.Context(0) as ctx:
+        d = torch.empty(frames * ch * bits // 8, dtype=torch.uint8, device="cuda:0")
+        ctx.synth_pcm_dev(seed, 0, frames, ch, bits, be, rate, 1.0, d)
+        ctx.synchronize()
+        return d.cpu().numpy().tobytes()
+
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LOWCUT = os.path.join(ROOT, "host", "lowcut")
@@ -28,7 +38,7 @@ def timed(*args):
 
 
 with tempfile.TemporaryDirectory(dir="/tmp") as d:
-    pcm = oracle.synth_pcm(1, 0, 14_400_000, 2, 24, False, 48000).tobytes()
+    pcm = synth(1, 14_400_000, 2, 24, False, 48000)
     w = os.path.join(d, "cfg4.wav")
     open(w, "wb").write(wav_bytes(pcm, 2, 24, 48000))
     dt, out = timed("-v", "-f", 20, "-s", 20, w, os.path.join(d, "cfg4_out.wav"))
@@ -42,7 +52,7 @@ with tempfile.TemporaryDirectory(dir="/tmp") as d:
         files.append(p)
     dt, _ = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"))
     print(f"batch of {NB} such files: {dt:.3f} s wall ({NB * 28.8 / dt:.0f} MSamples/s incl. file I/O and start-up)")
-    pcm = oracle.synth_pcm(2, 0, 26_460_000, 2, 16, True, 44100).tobytes()
+    pcm = synth(2, 26_460_000, 2, 16, True, 44100)
     a = os.path.join(d, "cfg2.aif")
     open(a, "wb").write(aiff_bytes(pcm, 2, 16, 44100.0))
     dt, out = timed("-v", "-n", "-f", 30, "-s", 10, a, os.path.join(d, "cfg2_out.aif"))
