@@ -89,6 +89,7 @@ AudioContainer::AudioContainer(const std::filesystem::path& path) : path_(path)
 	}
 	if (pcm_.channels < 1) throw FormatError(path.string() + ": no format chunk before the samples");
 	if (pcm_.payload_offset == 0) throw FormatError(path.string() + ": no sample chunk");
+	if (pcm_.payload_offset > size_) throw FormatError(path.string() + ": the sample chunk starts beyond the end of the file");
 	const uint64_t fb = (uint64_t) pcm_.channels * (pcm_.bits / 8);
 	// a truncated file keeps what is there; partial trailing frames are not samples
 	if (pcm_.payload_offset + pcm_.payload_bytes > size_)

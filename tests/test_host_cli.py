@@ -179,3 +179,41 @@ def test_cli_without_a_gpu_fails_loudly_never_falls_back(tmp_path):
     r = run(src, tmp_path / "out.wav")
     assert r.returncode == 1 and "no CPU path" in r.stderr
     assert not (tmp_path / "out.wav").exists()
+
+
+def test_container_parser_survives_malformed_files(tmp_path):
+    """Truncations and corrupted size fields: the parser must answer (exit 0 or a clean error,
+    exit 1) -- never crash, hang or read outside the file."""
+    rng = np.random.default_rng(2026)
+    seeds = [wav_bytes(rand_pcm(300, 2, 24), 2, 24, 48000), wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100, rf64=True),
+             aiff_bytes(rand_pcm(300, 2, 16), 2, 16, 44100.0, ssnd_offset=2),
+             aiff_bytes(rand_pcm(100, 1, 24), 1, 24, 48000.0, aifc=b"sowt", comm_last=True)]
+    n = 0
+    for si, data in enumerate(seeds):
+        hdr_len = min(len(data), 200)
+        variants = [data[:k] for k in (0, 3, 11, 12, 13, 20, 36, 43, 44, 45, len(data) // 2, len(data) - 1)]
+        for _ in range(40):
+            b = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, hdr_len))
+                b[pos] = int(rng.integers(0, 256))
+            variants.append(bytes(b))
+        # size fields blown up / zeroed
+        for pos in range(4, hdr_len - 4, 7):
+            b = bytearray(data)
+            b[pos:pos + 4] = b"\xff\xff\xff\xff" if pos % 2 else b"\0\0\0\0"
+            variants.append(bytes(b))
+        for vi, v in enumerate(variants):
+            p = tmp_path / f"m{si}_{vi}.bin"
+            p.write_bytes(v)
+            r = subprocess.run([TOOL, "info", str(p)], capture_output=True, text=True, timeout=10)
+            assert r.returncode in (0, 1), (si, vi, r.returncode, r.stderr[-200:])
+            if r.returncode == 0:
+                i = json.loads(r.stdout)
+                assert i["payload_offset"] + i["payload_bytes"] <= len(v)
+                assert i["frames"] * i["channels"] * i["bits"] // 8 == i["payload_bytes"]
+                q = tmp_path / "o.bin"
+                r2 = subprocess.run([TOOL, "invert", str(p), str(q)], capture_output=True, text=True, timeout=10)
+                assert r2.returncode in (0, 1)
+            n += 1
+    assert n > 200
