@@ -174,7 +174,28 @@ def cpu_reference_rate(cfg: dict, budget_s: float, threads: int | None = None):
 
 # --------------------------------------------------------------------- main ----------
 
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version
+    banner at communicator start-up, for one), so keep a private handle on the real stdout
+    for the result and point fd 1 at stderr for everybody else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> int:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -408,7 +429,7 @@ def main() -> int:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     return 0
 
@@ -453,7 +474,7 @@ def reference_arm(a, cfg, rank: int) -> int:
         "e2e": {"value": value, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
