@@ -193,7 +193,8 @@ def cpu_reference_rate(cfg: dict, budget_s: float, threads: int | None = None):
                    f"{taps.size}-tap kernel; " +
                    ("reference FilterCore.h apply_filter_range compiled in place (c_lib's fms()/taps behind "
                     "interface shims), " if use_ref else "oracle port of FilterCore.h (ref_f32 mode), ") +
-                   f"float32 buffers, {threads} std::threads per channel as ProcessFile.cp:64-83, -O3 AVX2/FMA"),
+                   f"float32 buffers, {threads} std::threads per channel as ProcessFile.cp:64-83, -O3 " +
+                   ("AVX-512" if use_ref and "avx512" in getattr(oracle.ref_lib(), "_path", "") else "AVX2/FMA")),
     }
     return msps, desc, t
 

@@ -21,6 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libref_filtercore.so")
+_REF_PATH_AVX512 = os.path.join(_HERE, "_ref", "libref_filtercore_avx512.so")
 
 _i64 = C.c_int64
 _dp = C.POINTER(C.c_double)
@@ -34,7 +35,8 @@ def build(force: bool = False) -> None:
         os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "fir_oracle.c"))
     ):
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
-    if os.path.exists("/root/reference/FilterCore.h") and (force or not os.path.exists(_REF_PATH)):
+    if os.path.exists("/root/reference/FilterCore.h") and (
+            force or not os.path.exists(_REF_PATH) or not os.path.exists(_REF_PATH_AVX512)):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
 
 
@@ -91,7 +93,14 @@ def ref_lib():
     """The reference's FilterCore.h build, or None where it was never built."""
     global _ref
     if _ref is None and os.path.exists(_REF_PATH):
-        R = C.CDLL(_REF_PATH)
+        path = _REF_PATH
+        try:  # the AVX-512 build of the same source where the host CPU has it (the CPU baseline's best shot)
+            if os.path.exists(_REF_PATH_AVX512) and " avx512f " in open("/proc/cpuinfo").read():
+                path = _REF_PATH_AVX512
+        except OSError:
+            pass
+        R = C.CDLL(path)
+        R._path = path
         R.ref_apply_filter_range.restype = None
         R.ref_apply_filter_range.argtypes = [_fp, C.c_longlong, _dp, C.c_longlong, _fp,
                                              C.c_longlong, C.c_longlong]
