@@ -589,3 +589,34 @@ def test_repeated_passes_do_not_leak_device_memory(oracle_mod):
         assert abs(torch.cuda.mem_get_info(0)[0] - free0) < (64 << 20)
         k1.free()
         k2.free()
+
+
+def test_torch_interop_stream_and_device_peak_view(oracle_mod):
+    """What bench.py and dist.py rely on: the context runs on a torch stream (torch events
+    bracket its work), and the device-resident peak scalar is viewable by torch without a copy
+    (the NCCL all-reduce runs on that view)."""
+    import torch
+
+    from audio_fir_filter_b200 import Context
+    from audio_fir_filter_b200.dist import _DevScalar, allreduce_max_peak
+
+    fs, ch, bits, frames = 8000, 2, 16, 300_000
+    pcm = oracle_mod.synth_pcm(1, 0, frames, ch, bits, False, fs)
+    d_in = torch.from_numpy(pcm).cuda()
+    with Context(0) as cx:
+        s = torch.cuda.Stream()
+        cx.set_stream(s.cuda_stream)
+        k = cx.build_kernel(40.0 / fs, 20.0 / fs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        cx.apply_dev(k, d_in, frames, ch, bits, False)
+        e1.record(s)
+        s.synchronize()
+        assert e0.elapsed_time(e1) >= cx.last_timing()["fir_ms"] > 0.0
+        t = torch.as_tensor(_DevScalar(cx.peak_dev()), device="cuda:0")
+        assert t.dtype == torch.float64 and float(t.item()) == cx.peak()
+        assert allreduce_max_peak(cx) == cx.peak()           # world size 1: no collective
+        cx.set_stream(None)                                   # back to the context's own stream
+        cx.apply_dev(k, d_in, frames, ch, bits, False)
+        assert cx.peak() == float(t.item())
+        k.free()
