@@ -42,3 +42,32 @@ def test_algorithmic_flop_count():
     # shorter than the kernel
     assert algorithmic_flop(3, 1, 5, 0, 0) == 2.0 * (3 + 3 + 3)
     assert kernel_order(10.0 / 44100) + 1 == 17641
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_full_contract_line():
+    """bench.py on the GPU (config 1, a few steps): exactly one JSON line with the base keys,
+    the e2e object, the roofline of the FIR kernel and the CPU baseline."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--config", "1",
+                        "--cpu-seconds", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "f64"
+    assert d["gpu_launches"] == 3 * 3                     # decode + FIR + encode per step, all ours
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["matches_device_arm"] is True
+    assert e["h2d_bytes_per_step"] == 2_880_000 * 6 and e["d2h_bytes_per_step"] == 2_880_000 * 6 + 8
+    rf = d["roofline"]
+    assert rf["kernel"] == "fir_dmma_kernel" and rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s"
+    assert 0.8 < rf["frac"] < 1.05 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown",
+                                                                         "sw_thermal_slowdown"}
