@@ -113,23 +113,40 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
+        import threading
+
         self.proc = None
+        self.lines = []
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
 
-    def stop(self) -> dict:
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def count_since(self, t0: float) -> int:
+        return sum(1 for t, _ in self.lines if t >= t0)
+
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Statistics over the samples taken between t0 and t1 (the timed region) when there
+        are at least three, else over every sample drawing at least half the peak power."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
+        self.thread.join(timeout=2)
+        inside = [l for t, l in self.lines if t0 <= t <= t1 + 0.12]
+        window = "timed region" if len(inside) >= 3 else "all samples under load"
+        out = "".join(inside if len(inside) >= 3 else [l for _, l in self.lines])
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
@@ -150,7 +167,7 @@ class ClockSampler:
         top = max(sm)
         load = [s for s, w in zip(sm, pw) if w >= 0.5 * max(pw)] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "sm_mhz_min": min(load), "sm_mhz_peak": top,
-                "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw), "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------- CPU baseline ----------
@@ -343,7 +360,19 @@ def main() -> int:
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if sampler else None
+    clocks = None
+    if sampler:
+        # a timed region shorter than a few sampler periods (config 1: ~3 ms a step) cannot be
+        # sampled: repeat the identical step untimed, right away, until the sampler has seen load
+        note = None
+        t_rep = t_end = time.perf_counter()
+        while sampler.count_since(t0) < 4 and time.perf_counter() - t_rep < 3.0 and world == 1:
+            step_dev()
+            t_end = time.perf_counter()
+            note = "timed region shorter than the sampling period: sampled over an identical untimed repeat right after it"
+        clocks = sampler.stop(t0, t_end)
+        if note:
+            clocks["note"] = note
     dev_ms = e0.elapsed_time(e1)
     tt = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
