@@ -211,6 +211,13 @@ void AudioContainer::parse_iff()
 	}
 }
 
+void AudioContainer::advise_willneed() const
+{
+#if defined(POSIX_FADV_WILLNEED)
+	(void) ::posix_fadvise(fd_, 0, (off_t) size_, POSIX_FADV_WILLNEED);
+#endif
+}
+
 void AudioContainer::read_payload(uint64_t offset, uint64_t n, void* dst) const
 {
 	if (offset + n > pcm_.payload_bytes) throw FormatError("payload read out of range");

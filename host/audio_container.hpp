@@ -52,6 +52,9 @@ public:
 	const std::vector<ChunkInfo>& chunks() const { return chunks_; }
 	uint64_t file_size() const { return size_; }
 
+	// Hint the kernel to start reading the file into the page cache (best effort).
+	void advise_willneed() const;
+
 	// Read payload bytes [offset, offset+n) (relative to the payload) into dst.
 	void read_payload(uint64_t offset, uint64_t n, void* dst) const;
 

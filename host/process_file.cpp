@@ -115,7 +115,7 @@ extern "C" void on_chunk_done(int64_t done_frames, int64_t, void* user)
 	b->bar->draw();
 }
 
-constexpr uint64_t PIECE_BYTES = 64ull << 20; // file <-> pinned buffer <-> device granularity
+constexpr uint64_t PIECE_BYTES = 16ull << 20; // file <-> pinned buffer <-> device granularity (pinning memory is slow: keep it small)
 
 // One sample block of the file on one GPU, streamed: file reads overlap upload and FIR.
 void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContainer& in, const Block& b, double* peak,
@@ -176,8 +176,12 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
               const std::vector<size_t>& slots)
 {
 	const auto t_start = std::chrono::steady_clock::now();
+	auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
 	auto status = [&](const std::string& s) {
 		if (opts.verbose) say(s);
+	};
+	auto stamp = [&](const char* what) {
+		if (opts.verbose) say(std::format("  [{:8.3f} s] {}", since(), what));
 	};
 
 	status("Opening input file.");                                   // ProcessFile.cp:33-35
@@ -207,6 +211,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		                   world > 1 ? std::format(", {} sample blocks of up to {} frames, halo {} frames each side", world,
 		                                           blocks[0].frames, ks[0]->half_len)
 		                             : std::string()));
+		stamp("kernel built");
 		status("Filtering.");
 		Progress bar;
 		bar.total = (int64_t) l.frames;
@@ -236,6 +241,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				}
 			});
 		sync.arrive_and_wait();
+		stamp("filtered, peak known");
 		try {
 			if (!failed) {
 				peak = *std::max_element(peaks.begin(), peaks.end());     // host max over the GPUs' peaks
@@ -248,9 +254,11 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 			errs.push_back(std::current_exception());
 			failed = true;
 		}
+		stamp("output file created");
 		sync.arrive_and_wait();
 		for (auto& t : th) t.join();
 		if (out_fd >= 0) AudioContainer::close_output(out_fd);
+		stamp("encoded and written");
 		for (auto& e : errs)
 			if (e) std::rethrow_exception(e);
 		for (size_t r = 0; r < world; ++r) status(std::format("  GPU {}:{}", r, timing_line(ctxs[r])));
@@ -335,6 +343,7 @@ static double fir_seconds(double taps, double frames, double channels)
 static double estimate_file_seconds(const std::filesystem::path& p, const FilterOptions& opts)
 {
 	AudioContainer in(p);
+	in.advise_willneed(); // start the read-ahead now: it runs while the CUDA context comes up
 	const PcmLayout& l = in.pcm();
 	if (!(l.sample_rate > 0.0) || !(opts.slope > 0.0)) return 0.0;
 	return fir_seconds(4.0 * l.sample_rate / opts.slope + 1.0, (double) l.frames, l.channels);
