@@ -85,6 +85,7 @@ SYMBOLS = {
     "fir_gpu_apply_end": (C.c_int, [_vp]),
     "fir_gpu_set_progress": (C.c_int, [_vp, _vp, _vp]),
     "fir_gpu_encode_range": (C.c_int, [_vp, C.c_double, _i64, _i64, _vp]),
+    "fir_gpu_process": (C.c_int, [_vp, _vp, _vp, C.POINTER(PcmFormat), C.c_int, _vp, _dp, _dp]),
     "fir_gpu_filter_f64": (C.c_int, [_vp, _vp, _dp, _i64, C.c_int32, _dp]),
     "fir_gpu_parked": (C.c_int, [_vp, _dp, _i64, C.c_int32]),
     "fir_gpu_parked_range": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int32]),
@@ -263,6 +264,15 @@ class Context:
             n = p.nbytes if isinstance(p, np.ndarray) else len(p)
             _check(lib().fir_gpu_apply_feed(self._h, _ptr(p) if n else None, n))
         _check(lib().fir_gpu_apply_end(self._h))
+
+    def process(self, kernel: Kernel, pcm_in, frames: int, channels: int, bits: int, big_endian: bool,
+                normalize: bool, pcm_out, halo_left: int = 0, halo_right: int = 0) -> tuple[float, float]:
+        """fir_gpu_process: the whole path of one host payload in one call -> (peak, scale)."""
+        fmt = self._fmt(frames, channels, bits, big_endian, halo_left, halo_right)
+        pk, sc = C.c_double(), C.c_double()
+        _check(lib().fir_gpu_process(self._h, kernel._h, _ptr(pcm_in) or None, C.byref(fmt), int(bool(normalize)),
+                                     _ptr(pcm_out) or None, C.byref(pk), C.byref(sc)))
+        return float(pk.value), float(sc.value)
 
     def set_progress(self, fn) -> None:
         """fn(done_frames, total_frames) or None.  Called from a CUDA callback thread."""

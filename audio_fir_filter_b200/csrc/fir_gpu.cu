@@ -146,6 +146,10 @@ struct fir_gpu_ctx {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // H2D of the next chunk runs under the FIR of the current one
 	cudaEvent_t copy_done = nullptr, pcm_free = nullptr, feed_last = nullptr;
+	cudaStream_t d2h_stream = nullptr; // speculative downloads of fir_gpu_process run under the FIR
+	cudaEvent_t spec_done = nullptr;
+	unsigned char* d_out = nullptr;    // encoded PCM of the chunks already filtered (fir_gpu_process)
+	size_t out_cap = 0;
 	PFN_encodeTiled encode_tiled = nullptr;
 
 	unsigned char* d_pcm = nullptr;
@@ -169,6 +173,7 @@ struct fir_gpu_ctx {
 		size_t bytes_fed = 0;  // of the host payload, uploaded or in flight
 		size_t bytes_total = 0;
 		int64_t done_frames = 0;
+		unsigned char* spec_out = nullptr; // host buffer that receives each chunk encoded with scale 1 (or null)
 	} pass;
 	fir_gpu_progress_fn progress = nullptr;
 	void* progress_user = nullptr;
@@ -419,6 +424,8 @@ int fir_gpu_create(int device, fir_gpu_ctx** out)
 	CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
 	CU_TRY(cudaEventCreateWithFlags(&c->pcm_free, cudaEventDisableTiming));
 	CU_TRY(cudaEventCreateWithFlags(&c->feed_last, cudaEventDisableTiming));
+	CU_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+	CU_TRY(cudaEventCreateWithFlags(&c->spec_done, cudaEventDisableTiming));
 	CU_TRY(cudaMalloc(&c->d_peak, 64));
 	CU_TRY(cudaMemset(c->d_peak, 0, 64));
 	CU_TRY(cudaMalloc(&c->d_sink, 8));
@@ -454,6 +461,9 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 	if (c->copy_done) cudaEventDestroy(c->copy_done);
 	if (c->pcm_free) cudaEventDestroy(c->pcm_free);
 	if (c->feed_last) cudaEventDestroy(c->feed_last);
+	if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+	if (c->spec_done) cudaEventDestroy(c->spec_done);
+	cudaFree(c->d_out);
 	for (ProgressNote* n : c->notes) delete n;
 	delete c;
 }
@@ -633,7 +643,8 @@ void fir_gpu_kernel_free(fir_gpu_kernel* k)
 // upload of everything else hides under its FIR (and under the FIRs that follow);
 // a streamed apply (feed by feed) is cut into ~16 chunks that start as their bytes land.
 static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c, const FirVariant& v, int64_t frames,
-                                                            int ch, int64_t n_taps, int mode /*0 dev,1 host,2 stream*/)
+                                                            int ch, int64_t n_taps,
+                                                            int mode /*0 dev, 1 host, 2 stream, 3 host + speculative out*/)
 {
 	const int64_t t_out = v.t_out;
 	int64_t chunk = (c->x_budget_bytes / 8 / ch - (n_taps + 2 * MAX_KT)) / t_out * t_out;
@@ -646,6 +657,8 @@ static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c
 		f0 = first;
 	}
 	if (mode == 2 && frames >= 256 * t_out) chunk = std::min(chunk, round_up(frames / 16, t_out));
+	if (mode == 3 && frames >= 64 * t_out) // speculative downloads: a dozen chunks, each still many waves long
+		chunk = std::min(chunk, round_up(frames / (frames >= 1024 * t_out ? 12 : 4), t_out));
 	for (; f0 < frames; f0 += chunk) out.emplace_back(f0, std::min(chunk, frames - f0));
 	return out;
 }
@@ -737,6 +750,25 @@ static int pass_launch_ready(fir_gpu_ctx* c)
 		end_span(c, s);
 		c->t_fir.push_back(s);
 		if (rc) return rc;
+		if (p.spec_out) {
+			// speculate that the file needs no rescaling (peak <= 1, no -n): encode this chunk
+			// with scale 1 right away and download it under the FIR of the next chunk
+			unsigned char* dst = c->d_out + (size_t) f0 * fb;
+			s = begin_span(c);
+			DISPATCH_CODEC(launch_encode, fmt.bits, fmt.big_endian != 0, c, c->d_y + f0, c->y_pitch, nf, ch,
+			               std::ldexp(1.0, fmt.bits - 1), dst);
+			end_span(c, s);
+			c->t_encode.push_back(s);
+			c->other_launches++;
+			CU_TRY(cudaGetLastError());
+			CU_TRY(cudaEventRecord(c->spec_done, c->stream));
+			CU_TRY(cudaStreamWaitEvent(c->d2h_stream, c->spec_done, 0));
+			s = begin_span(c, c->d2h_stream);
+			CU_TRY(cudaMemcpyAsync(p.spec_out + (size_t) f0 * fb, dst, (size_t) nf * fb, cudaMemcpyDeviceToHost,
+			                       c->d2h_stream));
+			end_span(c, s, c->d2h_stream);
+			c->t_d2h.push_back(s);
+		}
 		p.done_frames = f0 + nf;
 		if (c->progress) {
 			ProgressNote* n = new ProgressNote{c->progress, c->progress_user, p.done_frames, fmt.frames};
@@ -769,6 +801,25 @@ static int check_apply_args(fir_gpu_ctx* c, const fir_gpu_kernel* k, const fir_g
 	return check_fmt(fmt);
 }
 
+// Upload the host payload range by range, each just ahead of the chunk that needs it.
+static int pass_feed_all(fir_gpu_ctx* c, const unsigned char* src, const fir_gpu_pcm* fmt, size_t in_bytes)
+{
+	const size_t fb = (size_t) fmt->channels * (fmt->bits / 8);
+	const int64_t H = (c->pass.k->n_taps - 1) / 2;
+	for (const auto& [f0, nf] : c->pass.chunks) {
+		const int64_t need = std::min(fmt->frames + fmt->halo_right, f0 + nf + H) + fmt->halo_left; // frames from byte 0
+		const size_t upto = std::min(in_bytes, (size_t) need * fb);
+		if (upto > c->pass.bytes_fed) {
+			int rc = pass_upload(c, src + c->pass.bytes_fed, upto - c->pass.bytes_fed);
+			if (!rc) rc = pass_launch_ready(c);
+			if (rc) return rc;
+		}
+	}
+	if (c->pass.bytes_fed < in_bytes) // halo_right beyond half_len: not needed by any chunk
+		return pass_upload(c, src + c->pass.bytes_fed, in_bytes - c->pass.bytes_fed);
+	return FIR_GPU_OK;
+}
+
 int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host, const fir_gpu_pcm* fmt)
 {
 	int rc = check_apply_args(c, k, fmt);
@@ -782,22 +833,8 @@ int fir_gpu_apply(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_host,
 	if (rc) return rc;
 	rc = pass_begin(c, k, c->d_pcm, fmt, 1);
 	if (rc) return rc;
-	// upload range by range, just ahead of the chunk that needs it
-	const int64_t H = (k->n_taps - 1) / 2;
-	const unsigned char* src = static_cast<const unsigned char*>(pcm_host);
-	for (const auto& [f0, nf] : c->pass.chunks) {
-		const int64_t need = std::min(fmt->frames + fmt->halo_right, f0 + nf + H) + fmt->halo_left; // frames from byte 0
-		const size_t upto = std::min(in_bytes, (size_t) need * fb);
-		if (upto > c->pass.bytes_fed) {
-			rc = pass_upload(c, src + c->pass.bytes_fed, upto - c->pass.bytes_fed);
-			if (!rc) rc = pass_launch_ready(c);
-			if (rc) return rc;
-		}
-	}
-	if (c->pass.bytes_fed < in_bytes) { // halo_right beyond half_len: not needed by any chunk
-		rc = pass_upload(c, src + c->pass.bytes_fed, in_bytes - c->pass.bytes_fed);
-		if (rc) return rc;
-	}
+	rc = pass_feed_all(c, static_cast<const unsigned char*>(pcm_host), fmt, in_bytes);
+	if (rc) return rc;
 	return pass_end(c);
 }
 
@@ -811,6 +848,42 @@ int fir_gpu_apply_dev(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_d
 	rc = pass_begin(c, k, static_cast<const unsigned char*>(pcm_dev), fmt, 0);
 	if (rc) return rc;
 	return pass_end(c);
+}
+
+int fir_gpu_process(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_in_host, const fir_gpu_pcm* fmt,
+                    int normalize, void* pcm_out_host, double* peak_out, double* scale_out)
+{
+	int rc = check_apply_args(c, k, fmt);
+	if (rc) return rc;
+	if ((!pcm_in_host || !pcm_out_host) && fmt->frames > 0) return fail(FIR_GPU_ERR_INVALID, "null PCM buffer");
+	DeviceGuard g(c->device);
+	reset_timing(c, true);
+	const size_t fb = (size_t) fmt->channels * (fmt->bits / 8);
+	const size_t in_bytes = (size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fb;
+	const size_t out_bytes = (size_t) fmt->frames * fb;
+	const bool speculate = !normalize && fmt->frames > 0;
+	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, in_bytes + 32);
+	if (!rc && speculate) rc = ensure((void**) &c->d_out, &c->out_cap, out_bytes + 32);
+	if (rc) return rc;
+	rc = pass_begin(c, k, c->d_pcm, fmt, speculate ? 3 : 1);
+	if (rc) return rc;
+	c->pass.spec_out = speculate ? static_cast<unsigned char*>(pcm_out_host) : nullptr;
+	rc = pass_feed_all(c, static_cast<const unsigned char*>(pcm_in_host), fmt, in_bytes);
+	if (!rc) rc = pass_end(c);
+	if (rc) return rc;
+	double pk = 0.0;
+	rc = fir_gpu_peak(c, &pk); // waits for the FIR
+	if (rc) return rc;
+	// ProcessFile.cp:98: normalise when the peak exceeds full scale or -n is given
+	const double sc = ((pk > 1.0 || normalize) && pk > 0.0) ? 1.0 / pk : 1.0;
+	if (speculate) CU_TRY(cudaStreamSynchronize(c->d2h_stream)); // the scale-1 PCM is in pcm_out_host
+	if ((!speculate || sc != 1.0) && fmt->frames > 0) {
+		rc = fir_gpu_encode(c, sc, pcm_out_host); // the speculation lost (or was not made): encode for real
+		if (rc) return rc;
+	}
+	if (peak_out) *peak_out = pk;
+	if (scale_out) *scale_out = sc;
+	return FIR_GPU_OK;
 }
 
 // ---- streamed apply: the payload arrives piece by piece (file reads overlap the GPU) ----

@@ -70,10 +70,11 @@ def process_pcm(ctx: capi.Context, pcm_in, info: PcmInfo, opts: FilterOptions, p
         # ProcessFile.cp:48-49: both arguments are normalised by the sample rate.
         kernel = ctx.build_kernel(opts.freq / info.sample_rate, opts.slope / info.sample_rate)
     try:
-        ctx.apply(kernel, pcm_in, info.frames, info.channels, info.bits, info.big_endian)
-        peak = ctx.peak()
-        scale = scale_for_peak(peak, opts.normalize)
-        ctx.encode(scale, pcm_out)
+        # one call: apply -> peak -> scale rule (ProcessFile.cp:98) -> encode, with the uploads
+        # and (without -n) the downloads running under the FIR
+        peak, scale = ctx.process(kernel, pcm_in, info.frames, info.channels, info.bits, info.big_endian,
+                                  opts.normalize, pcm_out)
+        assert scale == scale_for_peak(peak, opts.normalize)
         return {"peak": peak, "scale": scale, "half_len": kernel.half_len, "taps": kernel.num_taps}
     finally:
         if own:

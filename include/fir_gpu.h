@@ -188,6 +188,20 @@ FIR_GPU_API int fir_gpu_encode_range(fir_gpu_ctx *ctx, double scale, int64_t fir
 /* Same into device memory, asynchronous. */
 FIR_GPU_API int fir_gpu_encode_dev(fir_gpu_ctx *ctx, double scale, void *pcm_dev);
 
+/* ---- the whole path in one call ------------------------------------------- */
+
+/* process_file()'s arithmetic (ProcessFile.cp:41-101,117) for one payload in host
+ * memory: apply, peak, the scale rule of ProcessFile.cp:98 (normalise when the peak
+ * exceeds 1.0 or `normalize` is set), encode into pcm_out_host.  Same result as
+ * fir_gpu_apply + fir_gpu_peak + fir_gpu_encode, bit for bit; what it adds is overlap:
+ * without `normalize` it bets that the peak stays <= 1 (no rescaling), encodes each
+ * chunk as soon as it is filtered and downloads it under the FIR of the next chunk;
+ * only if the final peak exceeds 1 is everything encoded again with the real scale.
+ * Synchronous on return; the parked signal stays available. */
+FIR_GPU_API int fir_gpu_process(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const void *pcm_in_host,
+                                const fir_gpu_pcm *fmt, int normalize, void *pcm_out_host, double *peak,
+                                double *scale);
+
 /* ---- measurement & synthetic input --------------------------------------- */
 
 FIR_GPU_API int fir_gpu_last_timing(fir_gpu_ctx *ctx, fir_gpu_timing *t);

@@ -620,3 +620,29 @@ def test_torch_interop_stream_and_device_peak_view(oracle_mod):
         cx.apply_dev(k, d_in, frames, ch, bits, False)
         assert cx.peak() == float(t.item())
         k.free()
+
+
+@pytest.mark.parametrize("normalize,gain", [(False, 1.0), (True, 1.0), (False, 2.2), (True, 2.2)])
+def test_one_call_process_equals_the_three_calls(ctx, oracle_mod, normalize, gain):
+    """fir_gpu_process == fir_gpu_apply + fir_gpu_peak + scale rule + fir_gpu_encode, bit for bit --
+    whether its bet (no -n and peak <= 1 -> scale 1, download under the FIR) wins (gain 1.0) or
+    loses (gain 2.2 clips the input, the filtered peak exceeds 1 and everything is re-encoded)."""
+    from audio_fir_filter_b200 import scale_for_peak
+
+    fs, ch, bits, be, frames = 48000, 2, 24, False, 900_000
+    pcm = oracle_mod.synth_pcm(6, 0, frames, ch, bits, be, fs, gain=gain)
+    k = ctx.build_kernel(20.0 / fs, 100.0 / fs)
+    ctx.apply(k, pcm, frames, ch, bits, be)
+    pk = ctx.peak()
+    sc = scale_for_peak(pk, normalize)
+    want = np.empty_like(pcm)
+    ctx.encode(sc, want)
+    got = np.full_like(pcm, 0x5A)
+    pk2, sc2 = ctx.process(k, pcm, frames, ch, bits, be, normalize, got)
+    assert (pk2, sc2) == (pk, sc)
+    assert (pk > 1.0) == (gain > 2.0)
+    assert np.array_equal(got, want)
+    t = ctx.last_timing()
+    if not normalize:
+        assert t["fir_launches"] >= 4          # the speculative path filters chunk by chunk
+    k.free()
