@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -66,7 +67,7 @@ typedef void (*DmmaFn)(const double*, long long, const double*, int, double*, lo
 struct FirVariant {
 	const char* name;
 	int dmma; // 0: DFMA kernel (fir_fp64.cuh), 1: DMMA kernel (fir_dmma.cuh)
-	int nt, kt, t_out, box_rows, smem;
+	int nt, kt, t_out, box_rows, smem, ctas_per_sm;
 	DfmaFn dfma_kernel;
 	DmmaFn dmma_kernel;
 };
@@ -74,13 +75,13 @@ struct FirVariant {
 template <class Cfg>
 FirVariant dfma_variant(const char* name)
 {
-	return {name, 0, Cfg::NT, Cfg::KT, Cfg::T_OUT, Cfg::BOX_ROWS, Cfg::SMEM_BYTES, fir_fp64_kernel<Cfg>, nullptr};
+	return {name, 0, Cfg::NT, Cfg::KT, Cfg::T_OUT, Cfg::BOX_ROWS, Cfg::SMEM_BYTES, Cfg::MINB, fir_fp64_kernel<Cfg>, nullptr};
 }
 
 template <class Cfg>
 FirVariant dmma_variant(const char* name)
 {
-	return {name, 1, Cfg::NT, Cfg::KT, Cfg::T_OUT, 0, Cfg::SMEM_BYTES, nullptr, fir_dmma_kernel<Cfg>};
+	return {name, 1, Cfg::NT, Cfg::KT, Cfg::T_OUT, 0, Cfg::SMEM_BYTES, Cfg::MINB, nullptr, fir_dmma_kernel<Cfg>};
 }
 
 constexpr int MAX_KT = 1024; // tap arrays are zero-padded generously beyond any variant's tile
@@ -651,14 +652,23 @@ static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c
 	if (chunk < t_out) chunk = t_out;
 	std::vector<std::pair<int64_t, int64_t>> out;
 	int64_t f0 = 0;
+	if (mode == 2 && frames >= 256 * t_out) chunk = std::min(chunk, round_up(frames / 16, t_out));
+	if (mode == 3) {
+		// speculative downloads: one chunk per ~2.5 ms of FIR (35 TFLOP/s), at most 8, each a whole
+		// number of full waves of CTAs so that the extra launches do not add partial-wave tails
+		const double est_ms = 2.0 * (double) n_taps * (double) frames * ch / 35.0e9;
+		const int64_t n = std::clamp<int64_t>((int64_t) (est_ms / 2.5), 1, 8);
+		const int64_t wave = (int64_t) c->sm_count * v.ctas_per_sm;
+		const int64_t bx_unit = std::max<int64_t>(1, wave / std::gcd<int64_t>(wave, ch)); // grid.x per whole waves
+		const int64_t bx = round_up((frames / n + t_out - 1) / t_out, bx_unit);
+		if (n > 1) chunk = std::min(chunk, bx * t_out);
+		else mode = 1; // too short to split for the downloads: at least hide the upload
+	}
 	if (mode == 1 && frames >= 256 * t_out) {
 		const int64_t first = std::min(chunk, round_up(frames / 16, t_out));
 		out.emplace_back(0, first);
 		f0 = first;
 	}
-	if (mode == 2 && frames >= 256 * t_out) chunk = std::min(chunk, round_up(frames / 16, t_out));
-	if (mode == 3 && frames >= 64 * t_out) // speculative downloads: a dozen chunks, each still many waves long
-		chunk = std::min(chunk, round_up(frames / (frames >= 1024 * t_out ? 12 : 4), t_out));
 	for (; f0 < frames; f0 += chunk) out.emplace_back(f0, std::min(chunk, frames - f0));
 	return out;
 }
