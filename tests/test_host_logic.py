@@ -1,5 +1,4 @@
 """CPU tests of the host-side logic above the C-ABI (no device work)."""
-import numpy as np
 import pytest
 
 from audio_fir_filter_b200.process import FilterOptions, PcmInfo, plan_blocks, scale_for_peak

@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 import pytest
-import torch
+
 import torch.distributed as dist
 import torch.multiprocessing as mp
 

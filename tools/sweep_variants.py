@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from audio_fir_filter_b200 import capi  # noqa: E402
-from bench import CONFIGS, SEED, algorithmic_flop, kernel_order  # noqa: E402
+from bench import CONFIGS, SEED, algorithmic_flop  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=2)
