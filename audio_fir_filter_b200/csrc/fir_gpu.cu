@@ -701,6 +701,12 @@ static int pass_begin(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned ch
 	p.k = k;
 	p.pcm_dev = pcm_dev;
 	p.chunks = plan_chunks(c, variant_of(c), frames, ch, k->n_taps, mode);
+	// size the decoded-input scratch for the largest chunk now: growing it between chunks
+	// would mean a cudaFree, i.e. a device-wide synchronisation in the middle of the pass
+	int64_t max_pitch = 0;
+	for (const auto& [f0, nf] : p.chunks) max_pitch = std::max(max_pitch, x_pitch_for(variant_of(c), nf, k->n_taps));
+	rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) max_pitch * ch * sizeof(double));
+	if (rc) return rc;
 	p.bytes_total = (size_t) (fmt->halo_left + frames + fmt->halo_right) * ch * (fmt->bits / 8);
 	if (p.from_host) {
 		// the staging buffer may still be read by earlier work of the compute stream
