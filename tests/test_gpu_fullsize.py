@@ -50,7 +50,7 @@ def check_windows(ctx, oracle_mod, k, first_frame, frames, total_frames, ch, bit
     return worst, flips
 
 
-def run_config(ctx, oracle_mod, cfg_id, frames=None, W=1024, n_random=4):
+def run_config(ctx, oracle_mod, cfg_id, frames=None, W=1024, n_random=10):
     import torch
 
     c = CONFIGS[cfg_id]
@@ -107,7 +107,7 @@ def test_config4_one_file_full(ctx, oracle_mod):
 def test_config3_full_one_hour_eight_channels(ctx, oracle_mod):
     """1 h x 8 ch x 96 kHz, 192 001 taps: 1.06e15 FLOP, ~30 s of one B200; streams through the
     bounded FP64 input scratch in ~11 chunks and parks 22 GB."""
-    run_config(ctx, oracle_mod, 3, W=512, n_random=3)
+    run_config(ctx, oracle_mod, 3, W=512, n_random=12)
 
 
 def test_config5_slice_as_two_sample_blocks(ctx, oracle_mod):
@@ -144,7 +144,7 @@ def test_config5_slice_as_two_sample_blocks(ctx, oracle_mod):
         d_out = torch.empty(b.frames * fb, dtype=torch.uint8, device="cuda:0")
         cx.encode_dev(scale, d_out)
         cx.synchronize()
-        starts = [0, b.frames - W, b.frames // 2]
+        starts = [0, b.frames - W, b.frames // 2] + [int(v) for v in np.random.default_rng(b.rank).integers(0, b.frames - W, 5)]
         worst, flips = check_windows(cx, oracle_mod, k, base + b.start, b.frames, file_frames, ch, bits, be, fs,
                                      starts, W, d_out, scale)
         print(f"config 5 block {b.rank}: worst {worst:.2e}, {flips} flips, fir {cx.last_timing()['fir_ms']:.0f} ms")
