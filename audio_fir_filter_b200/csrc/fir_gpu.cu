@@ -161,6 +161,8 @@ struct fir_gpu_ctx {
 	size_t y_cap = 0;
 	unsigned long long* d_peak = nullptr;
 	double* d_sink = nullptr;
+	dd* d_lp = nullptr; // build_kernel scratch: low-pass taps (double-double) + block partial sums
+	size_t lp_cap = 0;
 
 	bool parked = false;
 
@@ -457,6 +459,7 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 	cudaFree(c->d_y);
 	cudaFree(c->d_peak);
 	cudaFree(c->d_sink);
+	cudaFree(c->d_lp);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->copy_done) cudaEventDestroy(c->copy_done);
@@ -571,22 +574,20 @@ int fir_gpu_build_kernel(fir_gpu_ctx* c, double fc_norm, double bw_norm, fir_gpu
 	int rc = alloc_kernel(c, M + 1, &k);
 	if (rc) return rc;
 	const int blocks = (int) ((M + 1 + 255) / 256);
-	dd* d_lp = nullptr;
-	dd* d_part = nullptr;
-	cudaError_t e = cudaMalloc(&d_lp, (size_t) (M + 1) * sizeof(dd));
-	if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t) (blocks + 1) * sizeof(dd));
-	if (e != cudaSuccess) {
-		cudaFree(d_lp);
+	// scratch kept by the context: a cudaFree per call would synchronise the whole device
+	// (and every other context working on it) once per file
+	rc = ensure((void**) &c->d_lp, &c->lp_cap, (size_t) (M + 1 + blocks + 1) * sizeof(dd));
+	if (rc) {
 		fir_gpu_kernel_free(k);
-		return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+		return rc;
 	}
+	dd* d_lp = c->d_lp;
+	dd* d_part = c->d_lp + (M + 1);
 	sinc_lowpass_kernel<<<blocks, 256, 0, c->stream>>>(M, fc_norm, d_lp, d_part);
 	sinc_sum_kernel<<<1, 256, 0, c->stream>>>(d_part, blocks, d_part + blocks);
 	sinc_lowcut_kernel<<<blocks, 256, 0, c->stream>>>(M, d_lp, d_part + blocks, k->d_taps, M + 1);
-	e = cudaGetLastError();
+	cudaError_t e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_lp);
-	cudaFree(d_part);
 	if (e != cudaSuccess) {
 		fir_gpu_kernel_free(k);
 		return fail(FIR_GPU_ERR_CUDA, std::string("build_kernel: ") + cudaGetErrorString(e));

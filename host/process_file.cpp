@@ -5,6 +5,7 @@
 #include <barrier>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <exception>
 #include <format>
 #include <iostream>
@@ -32,15 +33,6 @@ void check(int rc, const char* what)
 {
 	if (rc != FIR_GPU_OK) throw GpuError(rc, std::format("{}: {}", what, fir_gpu_last_error()));
 }
-
-struct KernelHandle {
-	fir_gpu_kernel* k = nullptr;
-	int64_t half_len = 0;
-	KernelHandle(fir_gpu_ctx* ctx, double fc, double bw) { check(fir_gpu_build_kernel(ctx, fc, bw, &k, &half_len), "fir_gpu_build_kernel"); }
-	~KernelHandle() { fir_gpu_kernel_free(k); }
-	KernelHandle(const KernelHandle&) = delete;
-	KernelHandle& operator=(const KernelHandle&) = delete;
-};
 
 fir_gpu_pcm make_fmt(const PcmLayout& l, int64_t frames, int64_t halo_l, int64_t halo_r)
 {
@@ -204,12 +196,13 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 	double scale = 1.0, peak = 0.0;
 	int out_fd = -1;
 	if (l.frames > 0) {
-		std::vector<std::unique_ptr<KernelHandle>> ks(world);
-		for (size_t r = 0; r < world; ++r) ks[r] = std::make_unique<KernelHandle>(ctxs[r], fc, bw);
-		const std::vector<Block> blocks = plan_blocks((int64_t) l.frames, world, ks[0]->half_len);
-		status(std::format("  {} taps{}", fir_gpu_kernel_num_taps(ks[0]->k),
+		std::vector<fir_gpu_kernel*> ks(world);
+		long long half_len = 0;
+		for (size_t r = 0; r < world; ++r) ks[r] = pool.kernel(slots[r], fc, bw, &half_len);
+		const std::vector<Block> blocks = plan_blocks((int64_t) l.frames, world, half_len);
+		status(std::format("  {} taps{}", fir_gpu_kernel_num_taps(ks[0]),
 		                   world > 1 ? std::format(", {} sample blocks of up to {} frames, halo {} frames each side", world,
-		                                           blocks[0].frames, ks[0]->half_len)
+		                                           blocks[0].frames, half_len)
 		                             : std::string()));
 		stamp("kernel built");
 		status("Filtering.");
@@ -225,7 +218,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 			th.emplace_back([&, r] {
 				const Block& b = blocks[r];
 				try {
-					if (b.frames) filter_block(ctxs[r], ks[r]->k, in, b, &peaks[r], &bar, pool, slots[r]);
+					if (b.frames) filter_block(ctxs[r], ks[r], in, b, &peaks[r], &bar, pool, slots[r]);
 				} catch (...) {
 					errs[r] = std::current_exception();
 					failed = true;
@@ -286,29 +279,31 @@ GpuPool::GpuPool(unsigned want)
 	forced_ = want != 0;
 	const int use = want == 0 ? n : std::min<int>((int) want, n);
 	for (int d = 0; d < use; ++d) ordinals_.push_back(d);
-	lanes_.resize(2 * ordinals_.size());
+	lanes_.resize(LANES * ordinals_.size());
 }
 
 GpuPool::~GpuPool()
 {
 	for (Lane& l : lanes_) {
+		for (const Lane::CachedKernel& c : l.kernels) fir_gpu_kernel_free(c.k);
 		for (unsigned char* b : l.buf) fir_gpu_host_free(b);
 		fir_gpu_destroy(l.ctx);
 	}
 }
 
-std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, bool both_subs, std::vector<size_t>* slots)
+std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, size_t subs, std::vector<size_t>* slots)
 {
 	n_devices = std::max<size_t>(1, std::min(n_devices, ordinals_.size()));
 	std::vector<size_t> want;
-	for (size_t sub = 0; sub < (both_subs ? 2u : 1u); ++sub)
-		for (size_t d = 0; d < n_devices; ++d) want.push_back(2 * d + sub);
+	subs = std::clamp<size_t>(subs, 1, LANES);
+	for (size_t sub = 0; sub < subs; ++sub)
+		for (size_t d = 0; d < n_devices; ++d) want.push_back(LANES * d + sub);
 	std::vector<std::thread> th;
 	std::vector<std::string> errs(lanes_.size());
 	for (size_t slot : want)
 		if (!lanes_[slot].ctx)
 			th.emplace_back([this, slot, &errs] {
-				if (fir_gpu_create(ordinals_[slot / 2], &lanes_[slot].ctx) != FIR_GPU_OK) errs[slot] = fir_gpu_last_error();
+				if (fir_gpu_create(ordinals_[slot / LANES], &lanes_[slot].ctx) != FIR_GPU_OK) errs[slot] = fir_gpu_last_error();
 			});
 	for (auto& t : th) t.join();
 	std::vector<fir_gpu_ctx*> out;
@@ -318,6 +313,22 @@ std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, bool both_subs, std
 	}
 	if (slots) *slots = want;
 	return out;
+}
+
+fir_gpu_kernel* GpuPool::kernel(size_t slot, double fc, double bw, long long* half_len)
+{
+	Lane& l = lanes_.at(slot); // a lane is used by one thread at a time: no lock
+	for (const Lane::CachedKernel& c : l.kernels)
+		if (c.fc == fc && c.bw == bw) {
+			*half_len = c.half_len;
+			return c.k;
+		}
+	fir_gpu_kernel* k = nullptr;
+	int64_t h = 0;
+	check(fir_gpu_build_kernel(l.ctx, fc, bw, &k, &h), "fir_gpu_build_kernel");
+	l.kernels.push_back({fc, bw, k, (long long) h});
+	*half_len = (long long) h;
+	return k;
 }
 
 unsigned char* GpuPool::staging(size_t slot, int which, size_t bytes)
@@ -362,7 +373,7 @@ void process_file(const std::filesystem::path& input_path, const std::filesystem
 {
 	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
 	std::vector<size_t> slots;
-	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, false, &slots);
+	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, 1, &slots);
 	run_file(input_path, output_path, opts, pool, ctxs, slots);
 }
 
@@ -372,9 +383,14 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 	double seconds = 0.0;
 	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
 	const size_t gpus = std::min(gpus_worth_starting(pool, seconds), jobs.size());
-	// two lanes per GPU: while one file filters, the other reads, uploads, downloads, writes
+	// several lanes per GPU: while one file filters, others read, upload, download, write.
+	// Per file the host side (page-cache read, output creation, write) costs a few times the
+	// FIR of a short file, so up to LANES files are in flight per GPU (LOWCUT_LANES overrides).
+	size_t lanes = GpuPool::LANES;
+	if (const char* e = std::getenv("LOWCUT_LANES")) lanes = (size_t) std::max(1, std::atoi(e));
 	std::vector<size_t> slots;
-	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(gpus, jobs.size() > gpus, &slots);
+	const std::vector<fir_gpu_ctx*> ctxs =
+		pool.acquire(gpus, std::min(lanes, (jobs.size() + gpus - 1) / gpus), &slots);
 	const size_t workers = std::min(ctxs.size(), jobs.size());
 	if (workers <= 1) {
 		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, {slots[0]});

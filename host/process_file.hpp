@@ -10,6 +10,7 @@
 #include <vector>
 
 struct fir_gpu_ctx;
+struct fir_gpu_kernel;
 
 namespace lowcut {
 
@@ -33,18 +34,29 @@ public:
 	GpuPool& operator=(const GpuPool&) = delete;
 	size_t limit() const { return ordinals_.size(); } // devices that may be used
 	bool forced() const { return forced_; }             // -g N given: use exactly that many when possible
-	// Lanes: two contexts per device (slot = 2*device + sub).  Block mode uses sub 0 of
-	// the first n devices; batch mode both subs, so that one file's I/O, upload and
-	// download overlap the other's FIR on the same GPU.  Created in parallel on demand.
-	std::vector<fir_gpu_ctx*> acquire(size_t n_devices, bool both_subs, std::vector<size_t>* slots = nullptr);
+	// Lanes: up to LANES contexts per device (slot = LANES*device + sub).  Block mode uses
+	// sub 0 of the first n devices; batch mode several subs, so that the file I/O, upload
+	// and download of some files overlap the FIR of another on the same GPU.  Created in
+	// parallel on demand.
+	static constexpr size_t LANES = 4;
+	std::vector<fir_gpu_ctx*> acquire(size_t n_devices, size_t subs, std::vector<size_t>* slots = nullptr);
 	// Two pinned buffers of `bytes` for upload and two for download, per lane, reused across files.
 	unsigned char* staging(size_t slot, int which /*0..3*/, size_t bytes);
+	// The low-cut kernel for (fc, bw) on that lane, built once and kept: files of one batch
+	// mostly share a sample rate (ProcessFile.cp:48-50 rebuilds it per file).
+	struct fir_gpu_kernel* kernel(size_t slot, double fc, double bw, long long* half_len);
 
 private:
 	struct Lane {
 		fir_gpu_ctx* ctx = nullptr;
 		unsigned char* buf[4] = {nullptr, nullptr, nullptr, nullptr};
 		size_t cap[4] = {0, 0, 0, 0};
+		struct CachedKernel {
+			double fc, bw;
+			struct fir_gpu_kernel* k;
+			long long half_len;
+		};
+		std::vector<CachedKernel> kernels;
 	};
 	std::vector<int> ordinals_;
 	std::vector<Lane> lanes_;

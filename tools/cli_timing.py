@@ -37,7 +37,7 @@ def timed(*args):
     return dt, r.stdout
 
 
-with tempfile.TemporaryDirectory(dir="/tmp") as d:
+with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/tmp")) as d:
     pcm = synth(1, 14_400_000, 2, 24, False, 48000)
     w = os.path.join(d, "cfg4.wav")
     open(w, "wb").write(wav_bytes(pcm, 2, 24, 48000))
