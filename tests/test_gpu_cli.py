@@ -116,3 +116,29 @@ def test_config1_full_size_file_through_the_cli(tmp_path, oracle_mod):
     assert r.returncode == 0, r.stderr
     nflip = check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, False, fs, 20.0, 20.0, False)
     print(f"config 1 through the CLI: {nflip} of {frames * ch} samples differ from the oracle by 1 LSB")
+
+
+@pytest.mark.parametrize("kind", ["rf64", "aifc_sowt", "aifc_none32", "aiff_comm_last"])
+def test_other_containers_end_to_end(tmp_path, oracle_mod, kind):
+    """RF64 (ds64 size fields), AIFF-C 'sowt' (little-endian) and 'NONE', COMM after SSND:
+    the layout the container layer reports is the one the device decodes with."""
+    frames = 50_000
+    if kind == "rf64":
+        fs, ch, bits, be, ext = 96000, 2, 24, False, ".wav"
+        build = lambda p: wav_bytes(p, ch, bits, fs, rf64=True)                      # noqa: E731
+    elif kind == "aifc_sowt":
+        fs, ch, bits, be, ext = 44100, 2, 16, False, ".aifc"
+        build = lambda p: aiff_bytes(p, ch, bits, float(fs), aifc=b"sowt")            # noqa: E731
+    elif kind == "aifc_none32":
+        fs, ch, bits, be, ext = 48000, 3, 32, True, ".aifc"
+        build = lambda p: aiff_bytes(p, ch, bits, float(fs), aifc=b"NONE", ssnd_offset=8)   # noqa: E731
+    else:
+        fs, ch, bits, be, ext = 48000, 1, 24, True, ".aif"
+        build = lambda p: aiff_bytes(p, ch, bits, float(fs), comm_last=True)          # noqa: E731
+    pcm = oracle_mod.synth_pcm(hash(kind) & 0xFFFF, 0, frames, ch, bits, be, fs).tobytes()
+    data = build(pcm)
+    src, dst = tmp_path / ("in" + ext), tmp_path / ("out" + ext)
+    src.write_bytes(data)
+    r = run("-f", 25, "-s", 250, "-n", src, dst)
+    assert r.returncode == 0, r.stderr
+    check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, be, fs, 25.0, 250.0, True)
