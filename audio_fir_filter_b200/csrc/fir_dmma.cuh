@@ -79,11 +79,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 //   xpad    : planar zero-padded input, channel pitch x_pitch doubles; readable up to
 //             gridDim.x*T_OUT + n_ktiles*KT per channel
 //   tpad    : TAP_PAD zeros, the M+1 taps, zeros up to n_ktiles*KT + 16 doubles
+//   n_steps : 8-tap steps that touch a real tap, floor((M+7)/8) + 1 <= n_ktiles*KT/8; the
+//             last tap tile stops there instead of multiplying its zero padding
 //   y, peak : as in fir_fp64_kernel
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 fir_dmma_kernel(const double* __restrict__ xpad, long long x_pitch, const double* __restrict__ tpad, int n_ktiles,
-                double* __restrict__ y, long long y_pitch, long long frames, unsigned long long* __restrict__ peak)
+                int n_steps, double* __restrict__ y, long long y_pitch, long long frames,
+                unsigned long long* __restrict__ peak)
 {
 	constexpr int T = Cfg::T, KT = Cfg::KT, STAGES = Cfg::STAGES;
 	constexpr int RING = 8 * (T - 1);
@@ -144,8 +147,10 @@ fir_dmma_kernel(const double* __restrict__ xpad, long long x_pitch, const double
 		}
 		const double* ap = xs + a_off + 64 * (T - 1);
 		const double* bp = ts + b_off;
-#pragma unroll 1
-		for (int j0 = 0; j0 < KT / 8; j0 += 8) {
+		const int steps = min(KT / 8, n_steps - i * (KT / 8)); // < KT/8 only in the last tile
+		// One trip = 8 steps (one full turn of the ring), unguarded so that the loads of all 8
+		// steps can be hoisted.  Every tile but the last runs a compile-time number of trips.
+		auto trip = [&](int j0) {
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				const double2 g = *reinterpret_cast<const double2*>(ap + 8 * (j0 + j));
@@ -163,6 +168,27 @@ fir_dmma_kernel(const double* __restrict__ xpad, long long x_pitch, const double
 #pragma unroll
 				for (int d = T - 2; d > 0; --d) ring[8 * d + j] = ring[8 * (d - 1) + j];
 				if (T > 1) ring[j] = g;
+			}
+		};
+		const int full = steps & ~7;
+		if (i + 1 < n_ktiles) {
+#pragma unroll
+			for (int j0 = 0; j0 < KT / 8; j0 += 8) trip(j0);
+		} else {
+#pragma unroll 1
+			for (int j0 = 0; j0 < full; j0 += 8) trip(j0);
+		}
+		// The up to 7 steps left in the LAST tile (the taps end there): no ring any more, every
+		// tile's fragment comes straight from the sample tile.
+#pragma unroll 1
+		for (int j = full; j < steps; ++j) {
+			const double be = bp[8 * j];
+			const double bo = bp[8 * j + 1];
+#pragma unroll
+			for (int t = 0; t < T; ++t) {
+				const double2 g = *reinterpret_cast<const double2*>(xs + a_off + 64 * t + 8 * j);
+				dmma(acc[t], g.x, be);
+				dmma(acc[t], g.y, bo);
 			}
 		}
 		__syncthreads();

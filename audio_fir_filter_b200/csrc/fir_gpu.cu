@@ -61,7 +61,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // ---- FIR kernel variants ------------------------------------------------------
 
 typedef void (*DfmaFn)(const CUtensorMap, const double*, int, double*, long long, long long, unsigned long long*);
-typedef void (*DmmaFn)(const double*, long long, const double*, int, double*, long long, long long,
+typedef void (*DmmaFn)(const double*, long long, const double*, int, int, double*, long long, long long,
                        unsigned long long*);
 
 struct FirVariant {
@@ -348,7 +348,8 @@ int launch_fir(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* d_x, int64
 	dim3 grid((unsigned) ((frames + v.t_out - 1) / v.t_out), (unsigned) ch);
 	if (v.dmma) {
 		const int n_ktiles = (int) ((k->n_taps + 7 + v.kt - 1) / v.kt);
-		v.dmma_kernel<<<grid, v.nt, v.smem, c->stream>>>(d_x, (long long) x_pitch, k->d_tpad, n_ktiles, y,
+		const int n_steps = (int) ((k->n_taps - 1 + 7) / 8 + 1); // 8-tap steps that touch a real tap
+		v.dmma_kernel<<<grid, v.nt, v.smem, c->stream>>>(d_x, (long long) x_pitch, k->d_tpad, n_ktiles, n_steps, y,
 		                                               (long long) y_pitch, (long long) frames, peak);
 	} else {
 		CUtensorMap map;

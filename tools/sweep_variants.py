@@ -18,13 +18,15 @@ ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--frames", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--variants", default="")
+ap.add_argument("--slope", type=float, default=0.0, help="override the config's slope (tap count = 4*fs/slope + 1)")
 a = ap.parse_args()
 cfg = CONFIGS[a.config]
 frames = a.frames or cfg["frames"]
 fs, ch, bits, be = cfg["fs"], cfg["channels"], cfg["bits"], cfg["be"]
 ctx = capi.Context(0)
 print(json.dumps({"dfma_tflops": ctx.fp64_peak(0, 0.3), "dmma_tflops": ctx.fp64_peak(1, 0.3)}), flush=True)
-k = ctx.build_kernel(cfg["freq"] / fs, cfg["slope"] / fs)
+slope = a.slope or cfg["slope"]
+k = ctx.build_kernel(cfg["freq"] / fs, slope / fs)
 taps = k.num_taps
 d = torch.empty(frames * ch * bits // 8, dtype=torch.uint8, device="cuda:0")
 ctx.synth_pcm_dev(SEED, 0, frames, ch, bits, be, fs, 1.0, d)
@@ -38,5 +40,6 @@ for v in sel:
         ctx.apply_dev(k, d, frames, ch, bits, be)
         t = ctx.last_timing()
         best = t["fir_ms"] if best is None else min(best, t["fir_ms"])
-    print(json.dumps({"variant": v, "name": names[v], "fir_ms": best, "tflops": flop / best / 1e9,
-                      "decode_ms": t["decode_ms"], "peak": ctx.peak()}), flush=True)
+    print(json.dumps({"variant": v, "name": names[v], "taps": taps, "fir_ms": best, "tflops": flop / best / 1e9,
+                      "hbm_gbs": 16.0 * frames * ch / best / 1e6, "decode_ms": t["decode_ms"], "peak": ctx.peak()}),
+          flush=True)
