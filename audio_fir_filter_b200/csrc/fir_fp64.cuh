@@ -1,5 +1,8 @@
-// fir_fp64.cuh -- the direct FP64 FIR, the kernel that replaces
-// apply_filter_range() + WindowedSinc::fms() (reference FilterCore.h:20-79).
+// fir_fp64.cuh -- the direct FP64 FIR on the FP64 FMA pipe: the `dfma_*` variants of
+// the kernel that replaces apply_filter_range() + WindowedSinc::fms() (reference
+// FilterCore.h:20-79).  NOT the default: ncu shows the FMA pipe saturating at ~80 % of its
+// nominal rate (29 TFLOP/s), the DMMA formulation in fir_dmma.cuh reaches 99 % (36.9); this
+// kernel stays selectable (fir_gpu_set_variant) as the comparison point north_star asks for.
 //
 //   y[c][n] = sum_{k=0..M} h[k] * xpad[c][n + k],     xpad[c][j + H] = x[c][j]
 //
