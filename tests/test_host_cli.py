@@ -217,3 +217,47 @@ def test_container_parser_survives_malformed_files(tmp_path):
                 assert r2.returncode in (0, 1)
             n += 1
     assert n > 200
+
+
+def _random_riff(rng, pcm, ch, bits, rate):
+    """A WAVE file with random foreign chunks (random ids and sizes, odd ones padded) around fmt/data."""
+    import struct
+
+    nb = bits // 8
+
+    def chunk(cid, data):
+        return cid + struct.pack("<I", len(data)) + data + (b"\0" if len(data) & 1 else b"")
+
+    def junk():
+        cid = bytes(rng.integers(65, 91, 4).astype(np.uint8))          # 'A'..'Z'
+        if cid in (b"DATA", b"FMT ", b"DSSF"):
+            cid = b"XTRA"
+        return chunk(cid, rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8).tobytes())
+
+    body = b"".join(junk() for _ in range(int(rng.integers(0, 4))))
+    body += chunk(b"fmt ", struct.pack("<HHIIHH", 1, ch, rate, rate * ch * nb, ch * nb, bits))
+    body += b"".join(junk() for _ in range(int(rng.integers(0, 4))))
+    body += chunk(b"data", pcm)
+    body += b"".join(junk() for _ in range(int(rng.integers(0, 4))))
+    return b"RIFF" + struct.pack("<I", 4 + len(body)) + b"WAVE" + body
+
+
+def test_container_random_chunk_layouts_keep_every_foreign_byte(tmp_path):
+    rng = np.random.default_rng(7)
+    for case in range(40):
+        ch = int(rng.integers(1, 9))
+        bits = int(rng.choice([16, 24, 32]))
+        frames = int(rng.integers(0, 200))
+        pcm = rng.integers(0, 256, frames * ch * bits // 8, dtype=np.uint8).tobytes()
+        data = _random_riff(rng, pcm, ch, bits, 48000)
+        src, dst = tmp_path / f"r{case}.wav", tmp_path / f"r{case}_o.wav"
+        src.write_bytes(data)
+        i = info(src)
+        assert (i["channels"], i["bits"], i["frames"], i["payload_bytes"]) == (ch, bits, frames, len(pcm))
+        off = i["payload_offset"]
+        assert data[off:off + len(pcm)] == pcm
+        r = subprocess.run([TOOL, "invert", str(src), str(dst)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = dst.read_bytes()
+        assert out[:off] == data[:off] and out[off + len(pcm):] == data[off + len(pcm):]
+        assert out[off:off + len(pcm)] == bytes(b ^ 0xFF for b in pcm)

@@ -49,3 +49,21 @@ def test_assign_files_is_balanced_and_complete():
     loads = [sum(sizes[i] for i in lst) for lst in per]
     assert max(loads) - min(loads) <= max(sizes)
     assert assign_files([4] * 256, 8) == [[i for i in range(256) if i % 8 == r] for r in range(8)]
+
+
+def test_plan_blocks_random_inputs():
+    import random
+
+    rnd = random.Random(11)
+    for _ in range(500):
+        frames = rnd.choice([0, 1, 15, 16, 17, rnd.randrange(1, 10**6), rnd.randrange(1, 10**10)])
+        world = rnd.randrange(1, 17)
+        half = rnd.randrange(0, 200_000)
+        blocks = plan_blocks(frames, world, half)
+        assert len(blocks) == world and sum(b.frames for b in blocks) == frames
+        pos = 0
+        for b in blocks:
+            assert b.start == pos and 0 <= b.halo_left <= min(half, b.start)
+            assert b.halo_left == min(half, b.start) and b.halo_right == min(half, frames - b.start - b.frames)
+            assert b.start % 16 == 0 or b.frames == 0 or b.start == frames     # seams on 128-byte FP64 boundaries
+            pos += b.frames
