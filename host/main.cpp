@@ -54,6 +54,10 @@ int main(int argc, char** argv)
 				throw UsageError("With two parameters the second parameter must be a file path, not a directory.");
 			if (in.extension() != out.extension())
 				throw UsageError("Input and output file types (WAVE or AIFF) must be the same (extensions must match).");
+			// the reference removes an existing output BEFORE it opens the input (main.cp:107): with
+			// -O and input == output that destroys the only copy.  Refuse instead.
+			if (fs::exists(out) && fs::equivalent(in, out))
+				throw UsageError("Input and output are the same file: " + in.string());
 			if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
 			GpuPool pool(cli.gpus);
 			// main.cp:69-72 prints its resource line only when -v is NOT given; kept as is
@@ -83,6 +87,8 @@ int main(int argc, char** argv)
 				const fs::path& in = paths[i];
 				if (!fs::exists(in) || !fs::is_regular_file(in)) throw FileNotFound(in.string());
 				fs::path out = dest / in.filename();
+				if (fs::exists(out) && fs::equivalent(in, out))
+					throw UsageError("Input and output are the same file: " + in.string());
 				if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
 				jobs.emplace_back(in, out);
 			}

@@ -261,3 +261,19 @@ def test_container_random_chunk_layouts_keep_every_foreign_byte(tmp_path):
         out = dst.read_bytes()
         assert out[:off] == data[:off] and out[off + len(pcm):] == data[off + len(pcm):]
         assert out[off:off + len(pcm)] == bytes(b ^ 0xFF for b in pcm)
+
+
+def test_cli_refuses_to_overwrite_its_own_input(tmp_path):
+    """The reference deletes an existing output before opening the input (main.cp:107), so
+    `lowcut -O x.wav x.wav` would destroy x.wav; this host refuses (documented deviation)."""
+    src = tmp_path / "x.wav"
+    data = wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100)
+    src.write_bytes(data)
+    r = run("-O", src, src)
+    assert r.returncode == 1 and "same file" in r.stderr
+    assert src.read_bytes() == data
+    other = tmp_path / "y.wav"
+    other.write_bytes(data)
+    r = run("-O", src, other, tmp_path)          # batch into the inputs' own directory
+    assert r.returncode == 1 and "same file" in r.stderr
+    assert src.read_bytes() == data and other.read_bytes() == data
