@@ -184,6 +184,10 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 	                   l.big_endian ? "big-endian" : "little-endian", l.sample_rate, l.frames, in.chunks().size()));
 	if (!(l.sample_rate > 0.0)) throw FormatError(input_path.string() + ": sample rate is zero");
 	const double fc = opts.freq / l.sample_rate, bw = opts.slope / l.sample_rate; // ProcessFile.cp:48-49
+	// the output appears under its name only once it is complete (the reference writes in place and
+	// leaves a partial file behind when it fails)
+	std::filesystem::path part_path = output_path;
+	part_path += ".part";
 
 	// sample-block mode only pays when every GPU gets a sizeable block
 	size_t world = ctxs.size();
@@ -241,7 +245,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				scale = scale_for_peak(peak, opts.normalize);             // ProcessFile.cp:98-101
 				if (scale != 1.0) status("Doing audio normalize.");
 				status("Writing output file.");
-				out_fd = in.create_output(output_path);                   // every non-sample byte, verbatim
+				out_fd = in.create_output(part_path);                     // every non-sample byte, verbatim
 			}
 		} catch (...) {
 			errs.push_back(std::current_exception());
@@ -253,11 +257,17 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		if (out_fd >= 0) AudioContainer::close_output(out_fd);
 		stamp("encoded and written");
 		for (auto& e : errs)
-			if (e) std::rethrow_exception(e);
+			if (e) {
+				std::error_code ec;
+				std::filesystem::remove(part_path, ec); // never leave a half-written output behind
+				std::rethrow_exception(e);
+			}
+		std::filesystem::rename(part_path, output_path);
 		for (size_t r = 0; r < world; ++r) status(std::format("  GPU {}:{}", r, timing_line(ctxs[r])));
 	} else {
 		status("Writing output file.");
-		AudioContainer::close_output(in.create_output(output_path));
+		AudioContainer::close_output(in.create_output(part_path));
+		std::filesystem::rename(part_path, output_path);
 	}
 	status(std::format("  peak {:.9f}, scale {:.9f}, {:.3f} s", peak, scale,
 	                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count()));
