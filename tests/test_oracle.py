@@ -237,3 +237,29 @@ def test_process_whole_path_and_halo_blocks(oracle_mod):
     q = whole["pcm"].reshape(-1, 3)
     v = (q[:, 0].astype(np.int32) | (q[:, 1].astype(np.int32) << 8) | (q[:, 2].astype(np.int8).astype(np.int32) << 16))
     assert v.max() == (1 << 23) - 1 or v.min() == -(1 << 23)   # normalised to full scale
+
+
+def test_float32_faithful_mode_stays_within_one_lsb_of_the_fp64_mode(oracle_mod):
+    """Decision D1: the reference keeps float32 buffers (FilterCore.h:21-23,59,67,74); the parity bar is
+    the FP64/long-double mode.  At 16 and 24 bit the two modes' PCM differ by at most 1 LSB on a minority
+    of samples (5.7 % at 24 bit, 0.05 % at 16 bit on this signal); at 32 bit float32 cannot hold the sample."""
+    from test_gpu_parity import pcm_to_int
+
+    for bits, be, limit in [(24, False, 0.10), (16, True, 0.005)]:
+        fs, ch, frames = 48000, 2, 60_000
+        pcm = oracle_mod.synth_pcm(0xF1F1F1, 0, frames, ch, bits, be, fs)
+        hi = oracle_mod.process(pcm, frames, ch, bits, be, 20.0 / fs, 200.0 / fs, False)
+        taps = oracle_mod.build_lowcut(20.0 / fs, 200.0 / fs)
+        x32 = oracle_mod.decode(pcm, frames, ch, bits, be, dtype=np.float32)
+        y32 = np.stack([oracle_mod.fir_f32(x32[c], taps) for c in range(ch)])
+        p32 = oracle_mod.encode_f32(y32, 1.0, bits, be)
+        d = np.abs(pcm_to_int(p32, bits, be) - pcm_to_int(hi["pcm"], bits, be))
+        assert d.max() <= 1
+        assert np.count_nonzero(d) <= limit * d.size
+    # 32 bit: the float32 path is off by tens of LSB -- it is not a usable reference there
+    pcm = oracle_mod.synth_pcm(1, 0, 20_000, 1, 32, False, 48000)
+    hi = oracle_mod.process(pcm, 20_000, 1, 32, False, 20.0 / 48000, 200.0 / 48000, False)
+    x32 = oracle_mod.decode(pcm, 20_000, 1, 32, False, dtype=np.float32)
+    y32 = oracle_mod.fir_f32(x32[0], oracle_mod.build_lowcut(20.0 / 48000, 200.0 / 48000))[None, :]
+    d = np.abs(pcm_to_int(oracle_mod.encode_f32(y32, 1.0, 32, False), 32, False) - pcm_to_int(hi["pcm"], 32, False))
+    assert d.max() > 16
