@@ -651,3 +651,27 @@ def test_one_call_process_equals_the_three_calls(ctx, oracle_mod, normalize, gai
     if not normalize:
         assert t["fir_launches"] >= 2          # the speculative path filters chunk by chunk
     k.free()
+
+
+def test_out_of_memory_is_an_error_code_and_the_context_survives(ctx, oracle_mod):
+    """A payload whose parked FP64 signal cannot fit (8 TB) fails with FIR_GPU_ERR_NOMEM before any
+    kernel runs; the context keeps working afterwards."""
+    import torch
+
+    from audio_fir_filter_b200 import capi
+
+    fs, ch, bits = 8000, 2, 16
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)
+    small = oracle_mod.synth_pcm(2, 0, 10_000, ch, bits, False, fs)
+    d = torch.from_numpy(small).cuda()
+    with pytest.raises(capi.FirGpuError) as e:
+        ctx.apply_dev(k, d, 1 << 39, ch, bits, False)          # 2^39 frames x 2 ch x 8 B = 8 TB
+    assert e.value.code == capi.ERR_NOMEM
+    with pytest.raises(capi.FirGpuError) as e:
+        ctx.peak()                                              # nothing got parked
+    assert e.value.code == capi.ERR_STATE
+    out = np.empty_like(small)
+    pk, sc = ctx.process(k, small, 10_000, ch, bits, False, True, out)
+    want = oracle_mod.process(small, 10_000, ch, bits, False, 40.0 / fs, 50.0 / fs, True)
+    assert abs(pk - want["peak"]) <= 1e-12 * want["peak"] and np.array_equal(out, want["pcm"])
+    k.free()
