@@ -14,6 +14,10 @@
  *     fir_gpu_peak           <- the max_mag() loop                               ProcessFile.cp:92-96
  *     [host: scale rule  maxMag > 1 || normalize                                 ProcessFile.cp:98]
  *     fir_gpu_encode         <- AudioSamples::normalize + writeAll(buf, true)    ProcessFile.cp:100,117
+ *   or all of it in one call:
+ *     fir_gpu_process        <- ProcessFile.cp:41-101,117
+ *   or piece by piece (file reads / writes overlapping the GPU):
+ *     fir_gpu_apply_begin / _feed / _end, fir_gpu_encode_range, fir_gpu_set_progress
  *
  * Plain C: opaque handles, plain pointers and sizes, int status codes (0 = ok),
  * no exceptions across the boundary, no CPU fallback -- without a usable
