@@ -46,9 +46,11 @@ int fail(int code, const std::string& msg)
 #define CU_TRY(expr)                                                                              \
 	do {                                                                                          \
 		cudaError_t e_ = (expr);                                                                  \
-		if (e_ != cudaSuccess)                                                                    \
+		if (e_ != cudaSuccess) {                                                                  \
+			cudaGetLastError(); /* reported here: do not leave it for a later, unrelated call */ \
 			return fail(e_ == cudaErrorMemoryAllocation ? FIR_GPU_ERR_NOMEM : FIR_GPU_ERR_CUDA,   \
 			            std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+		}                                                                                         \
 	} while (0)
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -231,9 +233,12 @@ int ensure(void** p, size_t* cap, size_t need)
 	if (e != cudaSuccess) {
 		cudaGetLastError();
 		e = cudaMalloc(p, need + 256);
-		if (e != cudaSuccess)
+		if (e != cudaSuccess) {
+			cudaGetLastError(); // clear it: the failure is reported through the status code
+			*p = nullptr;
 			return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(need) +
 			                                   " B): " + cudaGetErrorString(e));
+		}
 		*cap = need + 256;
 		return FIR_GPU_OK;
 	}
@@ -547,6 +552,7 @@ static int alloc_kernel(fir_gpu_ctx* c, int64_t n_taps, fir_gpu_kernel** out)
 	cudaError_t e = cudaMalloc(&k->d_tpad, (size_t) k->n_alloc * sizeof(double));
 	if (e == cudaSuccess) e = cudaMemsetAsync(k->d_tpad, 0, (size_t) k->n_alloc * sizeof(double), c->stream);
 	if (e != cudaSuccess) {
+		cudaGetLastError();
 		cudaFree(k->d_tpad);
 		delete k;
 		return fail(FIR_GPU_ERR_NOMEM, std::string("cudaMalloc taps: ") + cudaGetErrorString(e));
