@@ -277,3 +277,26 @@ def test_cli_refuses_to_overwrite_its_own_input(tmp_path):
     r = run("-O", src, other, tmp_path)          # batch into the inputs' own directory
     assert r.returncode == 1 and "same file" in r.stderr
     assert src.read_bytes() == data and other.read_bytes() == data
+
+
+def test_cli_option_syntax_variants(tmp_path):
+    """boost::program_options' default style, which the reference's CLI gets through c_lib:
+    bundled switches, attached short values, --name=value, unambiguous prefixes, `--`."""
+    missing = tmp_path / "nope.wav"
+    out = tmp_path / "o.wav"
+    # every form parses: the run then fails on the missing input, not on the syntax
+    for args in (["-nvO", "-f20", "-s", "10"], ["--freq=20", "--slope", "10", "--norm"], ["-f", "20", "-t", "3", "-g", "1"],
+                 ["-Ons25", "--verb"], ["-f=20"]):
+        r = run(*args, missing, out)
+        assert r.returncode == 1 and r.stderr.startswith("File not found:") and "nope.wav" in r.stderr, (args, r.stderr)
+    # after `--` everything is a path, even if it looks like an option
+    r = run("-f", "20", "--", "-n", out)
+    assert r.returncode == 1 and "File not found: -n" in r.stderr
+    # errors
+    assert "ambiguous" not in run("--n", missing, out).stderr          # --n -> --normalize (only match)
+    r = run("--normalize=1", missing, out)
+    assert r.returncode == 1 and "does not take any arguments" in r.stderr
+    r = run("-t", "-1", missing, out)
+    assert r.returncode == 1 and "invalid" in r.stderr
+    r = run("-f", "1e", missing, out)
+    assert r.returncode == 1 and "invalid" in r.stderr
