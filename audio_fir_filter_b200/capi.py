@@ -60,7 +60,7 @@ class Timing(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
-# Every symbol include/fir_gpu.h declares: name -> (restype, argtypes).
+# Every symbol include/fir_gpu.h (the drop-in boundary) declares: name -> (restype, argtypes).
 _vp = C.c_void_p
 _i64 = C.c_int64
 _dp = C.POINTER(C.c_double)
@@ -74,7 +74,6 @@ SYMBOLS = {
     "fir_gpu_host_alloc": (_vp, [C.c_size_t]),
     "fir_gpu_host_free": (None, [_vp]),
     "fir_gpu_build_kernel": (C.c_int, [_vp, C.c_double, C.c_double, C.POINTER(_vp), C.POINTER(_i64)]),
-    "fir_gpu_kernel_from_taps": (C.c_int, [_vp, _dp, _i64, C.POINTER(_vp)]),
     "fir_gpu_kernel_num_taps": (_i64, [_vp]),
     "fir_gpu_kernel_taps": (C.c_int, [_vp, _vp, _dp, _i64]),
     "fir_gpu_kernel_free": (None, [_vp]),
@@ -95,12 +94,19 @@ SYMBOLS = {
     "fir_gpu_encode": (C.c_int, [_vp, C.c_double, _vp]),
     "fir_gpu_encode_dev": (C.c_int, [_vp, C.c_double, _vp]),
     "fir_gpu_last_timing": (C.c_int, [_vp, C.POINTER(Timing)]),
+}
+# include/fir_gpu_dev.h: measurement, synthetic input, tuning and test hooks (bench.py, tools/, tests/).
+DEV_SYMBOLS = {
+    "fir_gpu_kernel_from_taps": (C.c_int, [_vp, _dp, _i64, C.POINTER(_vp)]),
     "fir_gpu_synth_pcm_dev": (C.c_int, [_vp, C.c_uint64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32,
                                         _i64, C.c_double, _vp]),
     "fir_gpu_fp64_peak": (C.c_int, [_vp, C.c_int, C.c_double, _dp]),
+    "fir_gpu_copy_probe": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _dp]),
     "fir_gpu_set_variant": (C.c_int, [_vp, C.c_int]),
     "fir_gpu_variant_count": (C.c_int, []),
     "fir_gpu_variant_name": (C.c_char_p, [C.c_int]),
+    "fir_gpu_set_codec_geometry": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "fir_gpu_test_fail_next_create": (C.c_int, [C.c_int]),
     "fir_gpu_set_x_budget": (C.c_int, [_vp, _i64]),
 }
 
@@ -127,7 +133,7 @@ def lib() -> C.CDLL:
             raise FirGpuError(ERR_NO_DEVICE, f"{LIB_PATH} is missing: build it with "
                               "`make -C audio_fir_filter_b200/csrc` (no CPU fallback exists)")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in SYMBOLS.items():
+        for name, (res, args) in {**SYMBOLS, **DEV_SYMBOLS}.items():
             f = getattr(L, name)  # AttributeError if the header and library disagree
             f.restype = res
             f.argtypes = args
@@ -343,6 +349,15 @@ class Context:
         v = C.c_double()
         _check(lib().fir_gpu_fp64_peak(self._h, kind, seconds, C.byref(v)))
         return float(v.value)
+
+    def copy_probe(self, host_buf, nbytes: int, direction: int) -> float:
+        """One plain pinned copy of ``nbytes`` (0 = H2D, 1 = D2H) on the context's stream -> milliseconds."""
+        v = C.c_double()
+        _check(lib().fir_gpu_copy_probe(self._h, _ptr(host_buf), nbytes, direction, C.byref(v)))
+        return float(v.value)
+
+    def set_codec_geometry(self, tile_bytes: int, threads: int) -> None:
+        _check(lib().fir_gpu_set_codec_geometry(self._h, tile_bytes, threads))
 
     def set_variant(self, variant: int) -> None:
         _check(lib().fir_gpu_set_variant(self._h, variant))

@@ -14,14 +14,17 @@
 // There is no CPU fallback anywhere in this file: every entry point needs a
 // live sm_100 device.
 #include "../../include/fir_gpu.h"
+#include "../../include/fir_gpu_dev.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -36,6 +39,10 @@ using namespace firgpu;
 namespace {
 
 thread_local std::string g_err;
+
+// Test hook (fir_gpu_dev.h): the next n fir_gpu_create calls fail after their streams, events
+// and device buffers exist, to prove that a half-built context is torn down completely.
+std::atomic<int> fir_gpu_test_fail_create{0};
 
 int fail(int code, const std::string& msg)
 {
@@ -94,9 +101,13 @@ const FirVariant* fir_variants(int* n)
 	// Index 0 is the default: the best across configs 1, 2, 4, 5 in the sweeps on B200
 	// (tools/sweep_variants.py, profiles/r1_variant_sweep.txt): 36.9 TFLOP/s on config 2, 36.2 on config 1.
 	// The other shapes tried are in the sweep record; these are kept selectable.
+	// The product build carries the default and ONE FMA-pipe comparison kernel; the other shapes
+	// (2.3 MB of cubin the CLI would page in at start-up for nothing) need -DFIR_ALL_VARIANTS
+	// (`make -C audio_fir_filter_b200/csrc sweep`, used by tools/sweep_variants.py).
 	static const FirVariant v[] = {
 		dmma_variant<DmmaCfg<128, 2, 256, 3, 6>>("dmma_nt128_t2_kt256_s3_b6"),
 		dfma_variant<FirCfg<256, 512, 2, 2>>("dfma_nt256_kt512_s2_b2"),
+#ifdef FIR_ALL_VARIANTS
 		dfma_variant<FirCfg<256, 512, 3, 1>>("dfma_nt256_kt512_s3_b1"),
 		dfma_variant<FirCfg<128, 512, 2, 4>>("dfma_nt128_kt512_s2_b4"),
 		dmma_variant<DmmaCfg<128, 2, 128, 4, 6>>("dmma_nt128_t2_kt128_s4_b6"),
@@ -105,6 +116,7 @@ const FirVariant* fir_variants(int* n)
 		dmma_variant<DmmaCfg<256, 3, 512, 2, 2>>("dmma_nt256_t3_kt512_s2_b2"),
 		dmma_variant<DmmaCfg<128, 3, 128, 4, 4>>("dmma_nt128_t3_kt128_s4_b4"),
 		dmma_variant<DmmaCfg<64, 2, 128, 4, 12>>("dmma_nt64_t2_kt128_s4_b12"),
+#endif
 	};
 	*n = (int) (sizeof(v) / sizeof(v[0]));
 	return v;
@@ -149,8 +161,11 @@ struct fir_gpu_ctx {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // H2D of the next chunk runs under the FIR of the current one
 	cudaEvent_t copy_done = nullptr, pcm_free = nullptr, feed_last = nullptr;
-	cudaStream_t d2h_stream = nullptr; // speculative downloads of fir_gpu_process run under the FIR
-	cudaEvent_t spec_done = nullptr;
+	// Highest-priority stream for everything on the way OUT (encode to host + its download, the
+	// speculative downloads of fir_gpu_process): with several contexts on one GPU the output of
+	// one file gets SM slots and the copy engine ahead of the FIR CTAs of the next file.
+	cudaStream_t d2h_stream = nullptr;
+	cudaEvent_t spec_done = nullptr, enc_ready = nullptr;
 	unsigned char* d_out = nullptr;    // encoded PCM of the chunks already filtered (fir_gpu_process)
 	size_t out_cap = 0;
 	PFN_encodeTiled encode_tiled = nullptr;
@@ -182,7 +197,6 @@ struct fir_gpu_ctx {
 	} pass;
 	fir_gpu_progress_fn progress = nullptr;
 	void* progress_user = nullptr;
-	std::vector<ProgressNote*> notes;
 	fir_gpu_pcm fmt{};
 	int64_t y_pitch = 0;
 	int variant = 0;
@@ -195,6 +209,7 @@ struct fir_gpu_ctx {
 	int64_t x_budget_bytes = (int64_t) 2 << 30;
 	// cudaFuncSetAttribute is per device: remember what this context's device has
 	bool codec_attr[12] = {};
+	int codec_tile_bytes = CODEC_TILE_BYTES, codec_nt = CODEC_NT;
 	std::vector<char> fir_attr;
 };
 
@@ -246,19 +261,44 @@ int ensure(void** p, size_t* cap, size_t need)
 	return FIR_GPU_OK;
 }
 
-size_t begin_span(fir_gpu_ctx* c, cudaStream_t st = nullptr)
+// A timing span = two events of the context's pool around a piece of work.  Creating or
+// recording an event can fail (out of resources, a sticky error on the context): reported,
+// not ignored.
+int begin_span(fir_gpu_ctx* c, size_t* idx, cudaStream_t st = nullptr)
 {
 	if (c->pool_used == c->pool.size()) {
 		EventPair p;
-		cudaEventCreate(&p.a);
-		cudaEventCreate(&p.b);
+		CU_TRY(cudaEventCreate(&p.a));
+		cudaError_t e = cudaEventCreate(&p.b);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			cudaEventDestroy(p.a);
+			return fail(FIR_GPU_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+		}
 		c->pool.push_back(p);
 	}
-	cudaEventRecord(c->pool[c->pool_used].a, st ? st : c->stream);
-	return c->pool_used++;
+	CU_TRY(cudaEventRecord(c->pool[c->pool_used].a, st ? st : c->stream));
+	*idx = c->pool_used++;
+	return FIR_GPU_OK;
 }
 
-void end_span(fir_gpu_ctx* c, size_t i, cudaStream_t st = nullptr) { cudaEventRecord(c->pool[i].b, st ? st : c->stream); }
+int end_span(fir_gpu_ctx* c, size_t i, cudaStream_t st = nullptr)
+{
+	CU_TRY(cudaEventRecord(c->pool[i].b, st ? st : c->stream));
+	return FIR_GPU_OK;
+}
+
+#define SPAN_BEGIN(var, ...)                                  \
+	size_t var = 0;                                           \
+	do {                                                      \
+		int rc_ = begin_span(c, &var, ##__VA_ARGS__);         \
+		if (rc_) return rc_;                                  \
+	} while (0)
+#define SPAN_END(var, ...)                                    \
+	do {                                                      \
+		int rc_ = end_span(c, var, ##__VA_ARGS__);            \
+		if (rc_) return rc_;                                  \
+	} while (0)
 
 void reset_timing(fir_gpu_ctx* c, bool all)
 {
@@ -297,43 +337,52 @@ int check_fmt(const fir_gpu_pcm* f)
 }
 
 template <int BITS, bool BE>
-void launch_decode(fir_gpu_ctx* c, const unsigned char* pcm, int64_t avail_lo, int64_t avail_hi, int64_t g0,
-                   int64_t n_x, int ch, double* x, int64_t x_pitch)
+int launch_decode(fir_gpu_ctx* c, cudaStream_t st, const unsigned char* pcm, int64_t avail_lo, int64_t avail_hi,
+                  int64_t g0, int64_t n_x, int ch, double* x, int64_t x_pitch)
 {
 	const int fb = ch * (BITS / 8);
-	const int F = codec_tile_frames(fb);
-	const size_t smem = codec_smem_bytes(F * fb);
+	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
 	bool& attr_done = c->codec_attr[(BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
 	if (!attr_done) {
-		cudaFuncSetAttribute(pcm_decode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+		CU_TRY(cudaFuncSetAttribute(pcm_decode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                            CODEC_SMEM_MAX));
 		attr_done = true;
 	}
-	const unsigned blocks = (unsigned) ((n_x + F - 1) / F);
-	pcm_decode_kernel<BITS, BE><<<blocks, CODEC_NT, smem, c->stream>>>(pcm, avail_lo, avail_hi, g0, n_x, ch, x,
-	                                                                   x_pitch);
+	const int64_t tiles = (n_x + g.frames - 1) / g.frames;
+	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * g.ctas_per_sm);
+	pcm_decode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(pcm, avail_lo, avail_hi, g0, n_x, ch, x, x_pitch,
+	                                                          g.frames);
+	CU_TRY(cudaGetLastError());
+	c->other_launches++;
+	return FIR_GPU_OK;
 }
 
 template <int BITS, bool BE>
-void launch_encode(fir_gpu_ctx* c, const double* y, int64_t y_pitch, int64_t frames, int ch, double gain,
-                   unsigned char* pcm)
+int launch_encode(fir_gpu_ctx* c, cudaStream_t st, const double* y, int64_t y_pitch, int64_t frames, int ch,
+                  double gain, unsigned char* pcm)
 {
 	const int fb = ch * (BITS / 8);
-	const int F = codec_tile_frames(fb);
-	const size_t smem = codec_smem_bytes(F * fb);
+	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
 	bool& attr_done = c->codec_attr[6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
 	if (!attr_done) {
-		cudaFuncSetAttribute(pcm_encode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+		CU_TRY(cudaFuncSetAttribute(pcm_encode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                            CODEC_SMEM_MAX));
 		attr_done = true;
 	}
-	const unsigned blocks = (unsigned) ((frames + F - 1) / F);
-	pcm_encode_kernel<BITS, BE><<<blocks, CODEC_NT, smem, c->stream>>>(y, y_pitch, frames, ch, gain, pcm);
+	const int64_t tiles = (frames + g.frames - 1) / g.frames;
+	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * g.ctas_per_sm);
+	pcm_encode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(y, y_pitch, frames, ch, gain, pcm, g.frames);
+	CU_TRY(cudaGetLastError());
+	c->other_launches++;
+	return FIR_GPU_OK;
 }
 
-#define DISPATCH_CODEC(fn, bits, be, ...)                                  \
-	do {                                                                   \
-		if ((bits) == 16) { if (be) fn<16, true>(__VA_ARGS__); else fn<16, false>(__VA_ARGS__); } \
-		else if ((bits) == 24) { if (be) fn<24, true>(__VA_ARGS__); else fn<24, false>(__VA_ARGS__); } \
-		else { if (be) fn<32, true>(__VA_ARGS__); else fn<32, false>(__VA_ARGS__); } \
+// rc = fn<BITS, BE>(args...) for the format at hand
+#define DISPATCH_CODEC(rc, fn, bits, be, ...)                                  \
+	do {                                                                       \
+		if ((bits) == 16) rc = (be) ? fn<16, true>(__VA_ARGS__) : fn<16, false>(__VA_ARGS__);      \
+		else if ((bits) == 24) rc = (be) ? fn<24, true>(__VA_ARGS__) : fn<24, false>(__VA_ARGS__); \
+		else rc = (be) ? fn<32, true>(__VA_ARGS__) : fn<32, false>(__VA_ARGS__);                   \
 	} while (0)
 
 // One FIR launch over a zero-padded planar chunk resident at d_x (pitch from x_pitch_for).
@@ -424,7 +473,12 @@ int fir_gpu_create(int device, fir_gpu_ctx** out)
 		return fail(FIR_GPU_ERR_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
 
 	DeviceGuard g(device);
-	fir_gpu_ctx* c = new fir_gpu_ctx();
+	// a context that fails half-way is torn down again: nothing leaks
+	struct Destroyer {
+		void operator()(fir_gpu_ctx* p) const { fir_gpu_destroy(p); }
+	};
+	std::unique_ptr<fir_gpu_ctx, Destroyer> guard(new fir_gpu_ctx());
+	fir_gpu_ctx* c = guard.get();
 	c->device = device;
 	c->sm_count = prop.multiProcessorCount;
 	CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -433,21 +487,24 @@ int fir_gpu_create(int device, fir_gpu_ctx** out)
 	CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
 	CU_TRY(cudaEventCreateWithFlags(&c->pcm_free, cudaEventDisableTiming));
 	CU_TRY(cudaEventCreateWithFlags(&c->feed_last, cudaEventDisableTiming));
-	CU_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+	int prio_lo = 0, prio_hi = 0;
+	CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	CU_TRY(cudaStreamCreateWithPriority(&c->d2h_stream, cudaStreamNonBlocking, prio_hi));
 	CU_TRY(cudaEventCreateWithFlags(&c->spec_done, cudaEventDisableTiming));
+	CU_TRY(cudaEventCreateWithFlags(&c->enc_ready, cudaEventDisableTiming));
 	CU_TRY(cudaMalloc(&c->d_peak, 64));
 	CU_TRY(cudaMemset(c->d_peak, 0, 64));
-	CU_TRY(cudaMalloc(&c->d_sink, 8));
+	CU_TRY(cudaMalloc(&c->d_sink, 64));
+	if (fir_gpu_test_fail_create.load() > 0 && fir_gpu_test_fail_create.fetch_sub(1) > 0)
+		return fail(FIR_GPU_ERR_CUDA, "fir_gpu_create: injected failure (test hook)");
 
 	void* fn = nullptr;
 	cudaDriverEntryPointQueryResult qr;
 	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
-	if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
-		fir_gpu_destroy(c);
+	if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)
 		return fail(FIR_GPU_ERR_NO_DEVICE, "driver lacks cuTensorMapEncodeTiled (TMA)");
-	}
 	c->encode_tiled = (PFN_encodeTiled) fn;
-	*out = c;
+	*out = guard.release();
 	return FIR_GPU_OK;
 }
 
@@ -455,7 +512,9 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 {
 	if (!c) return;
 	DeviceGuard g(c->device);
-	cudaStreamSynchronize(c->stream);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+	if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
 	for (auto& p : c->pool) {
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
@@ -473,8 +532,9 @@ void fir_gpu_destroy(fir_gpu_ctx* c)
 	if (c->feed_last) cudaEventDestroy(c->feed_last);
 	if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
 	if (c->spec_done) cudaEventDestroy(c->spec_done);
+	if (c->enc_ready) cudaEventDestroy(c->enc_ready);
 	cudaFree(c->d_out);
-	for (ProgressNote* n : c->notes) delete n;
+	cudaGetLastError(); // teardown never leaves an error behind for an unrelated call
 	delete c;
 }
 
@@ -683,7 +743,8 @@ static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c
 
 static void CUDART_CB progress_trampoline(void* p)
 {
-	const ProgressNote* n = static_cast<const ProgressNote*>(p);
+	// the callback owns its note: nothing else has to guess when the stream got this far
+	std::unique_ptr<ProgressNote> n(static_cast<ProgressNote*>(p));
 	n->fn(n->done, n->total, n->user); // runs on a CUDA callback thread: no CUDA calls in there
 }
 
@@ -699,8 +760,6 @@ static int pass_begin(fir_gpu_ctx* c, const fir_gpu_kernel* k, const unsigned ch
 	int rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) c->y_pitch * ch * sizeof(double));
 	if (rc) return rc;
 	CU_TRY(cudaMemsetAsync(c->d_peak, 0, 8, c->stream));
-	for (ProgressNote* n : c->notes) delete n; // the previous pass has been synchronised by its peak / encode
-	c->notes.clear();
 
 	fir_gpu_ctx::Pass& p = c->pass;
 	p = fir_gpu_ctx::Pass();
@@ -729,10 +788,10 @@ static int pass_upload(fir_gpu_ctx* c, const unsigned char* src, size_t n)
 {
 	fir_gpu_ctx::Pass& p = c->pass;
 	if (!n) return FIR_GPU_OK;
-	size_t s = begin_span(c, c->copy_stream);
+	SPAN_BEGIN(s, c->copy_stream);
 	CU_TRY(cudaMemcpyAsync(const_cast<unsigned char*>(p.pcm_dev) + p.bytes_fed, src, n, cudaMemcpyHostToDevice,
 	                       c->copy_stream));
-	end_span(c, s, c->copy_stream);
+	SPAN_END(s, c->copy_stream);
 	c->t_h2d.push_back(s);
 	p.bytes_fed += n;
 	return FIR_GPU_OK;
@@ -762,42 +821,44 @@ static int pass_launch_ready(fir_gpu_ctx* c)
 		const int64_t x_pitch = x_pitch_for(v, nf, k->n_taps);
 		int rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) x_pitch * ch * sizeof(double));
 		if (rc) return rc;
-		size_t s = begin_span(c);
-		DISPATCH_CODEC(launch_decode, fmt.bits, fmt.big_endian != 0, c, p.pcm_dev, avail_lo, avail_hi, f0 - H, x_pitch,
-		               ch, c->d_x, x_pitch);
-		end_span(c, s);
-		c->t_decode.push_back(s);
-		c->other_launches++;
-		CU_TRY(cudaGetLastError());
-		s = begin_span(c);
-		rc = launch_fir(c, k, c->d_x, x_pitch, ch, c->d_y + f0, c->y_pitch, nf, c->d_peak);
-		end_span(c, s);
-		c->t_fir.push_back(s);
+		SPAN_BEGIN(sd);
+		DISPATCH_CODEC(rc, launch_decode, fmt.bits, fmt.big_endian != 0, c, c->stream, p.pcm_dev, avail_lo, avail_hi,
+		               f0 - H, x_pitch, ch, c->d_x, x_pitch);
 		if (rc) return rc;
+		SPAN_END(sd);
+		c->t_decode.push_back(sd);
+		SPAN_BEGIN(sf);
+		rc = launch_fir(c, k, c->d_x, x_pitch, ch, c->d_y + f0, c->y_pitch, nf, c->d_peak);
+		if (rc) return rc;
+		SPAN_END(sf);
+		c->t_fir.push_back(sf);
 		if (p.spec_out) {
 			// speculate that the file needs no rescaling (peak <= 1, no -n): encode this chunk
-			// with scale 1 right away and download it under the FIR of the next chunk
+			// with scale 1 as soon as it is filtered (on the high-priority output stream, so it
+			// does not queue behind the next chunk's FIR) and download it under that FIR
 			unsigned char* dst = c->d_out + (size_t) f0 * fb;
-			s = begin_span(c);
-			DISPATCH_CODEC(launch_encode, fmt.bits, fmt.big_endian != 0, c, c->d_y + f0, c->y_pitch, nf, ch,
-			               std::ldexp(1.0, fmt.bits - 1), dst);
-			end_span(c, s);
-			c->t_encode.push_back(s);
-			c->other_launches++;
-			CU_TRY(cudaGetLastError());
 			CU_TRY(cudaEventRecord(c->spec_done, c->stream));
 			CU_TRY(cudaStreamWaitEvent(c->d2h_stream, c->spec_done, 0));
-			s = begin_span(c, c->d2h_stream);
+			SPAN_BEGIN(se, c->d2h_stream);
+			DISPATCH_CODEC(rc, launch_encode, fmt.bits, fmt.big_endian != 0, c, c->d2h_stream, c->d_y + f0, c->y_pitch,
+			               nf, ch, std::ldexp(1.0, fmt.bits - 1), dst);
+			if (rc) return rc;
+			SPAN_END(se, c->d2h_stream);
+			c->t_encode.push_back(se);
+			SPAN_BEGIN(sc, c->d2h_stream);
 			CU_TRY(cudaMemcpyAsync(p.spec_out + (size_t) f0 * fb, dst, (size_t) nf * fb, cudaMemcpyDeviceToHost,
 			                       c->d2h_stream));
-			end_span(c, s, c->d2h_stream);
-			c->t_d2h.push_back(s);
+			SPAN_END(sc, c->d2h_stream);
+			c->t_d2h.push_back(sc);
 		}
 		p.done_frames = f0 + nf;
 		if (c->progress) {
 			ProgressNote* n = new ProgressNote{c->progress, c->progress_user, p.done_frames, fmt.frames};
-			c->notes.push_back(n);
-			CU_TRY(cudaLaunchHostFunc(c->stream, progress_trampoline, n));
+			const cudaError_t pe = cudaLaunchHostFunc(c->stream, progress_trampoline, n);
+			if (pe != cudaSuccess) {
+				delete n; // never enqueued
+				CU_TRY(pe);
+			}
 		}
 		++p.next;
 	}
@@ -891,6 +952,15 @@ int fir_gpu_process(fir_gpu_ctx* c, const fir_gpu_kernel* k, const void* pcm_in_
 	if (rc) return rc;
 	rc = pass_begin(c, k, c->d_pcm, fmt, speculate ? 3 : 1);
 	if (rc) return rc;
+	// Once downloads into pcm_out_host may be in flight, no exit path may return before they
+	// have landed (or failed): the caller is free to reuse or free that buffer on return.
+	struct DrainOnExit {
+		cudaStream_t st;
+		~DrainOnExit()
+		{
+			if (st && cudaStreamSynchronize(st) != cudaSuccess) cudaGetLastError();
+		}
+	} drain{speculate ? c->d2h_stream : nullptr};
 	c->pass.spec_out = speculate ? static_cast<unsigned char*>(pcm_out_host) : nullptr;
 	rc = pass_feed_all(c, static_cast<const unsigned char*>(pcm_in_host), fmt, in_bytes);
 	if (!rc) rc = pass_end(c);
@@ -978,11 +1048,11 @@ int fir_gpu_filter_f64(fir_gpu_ctx* c, const fir_gpu_kernel* k, const double* x_
 	CU_TRY(cudaMemsetAsync(c->d_x, 0, (size_t) x_pitch * channels * sizeof(double), c->stream));
 	CU_TRY(cudaMemcpy2DAsync(c->d_x + H, (size_t) x_pitch * 8, x_host, (size_t) frames * 8, (size_t) frames * 8,
 	                         (size_t) channels, cudaMemcpyHostToDevice, c->stream));
-	size_t s = begin_span(c);
+	SPAN_BEGIN(s);
 	rc = launch_fir(c, k, c->d_x, x_pitch, channels, c->d_y, c->y_pitch, frames, c->d_peak);
-	end_span(c, s);
-	c->t_fir.push_back(s);
 	if (rc) return rc;
+	SPAN_END(s);
+	c->t_fir.push_back(s);
 	CU_TRY(cudaMemcpy2DAsync(y_host, (size_t) frames * 8, c->d_y, (size_t) c->y_pitch * 8, (size_t) frames * 8,
 	                         (size_t) channels, cudaMemcpyDeviceToHost, c->stream));
 	CU_TRY(cudaStreamSynchronize(c->stream));
@@ -1053,10 +1123,10 @@ int fir_gpu_peak_recompute(fir_gpu_ctx* c, double* peak)
 		const int64_t pairs = c->fmt.frames / 2;
 		unsigned bx = (unsigned) std::min<int64_t>((pairs + 255) / 256, (int64_t) c->sm_count * 8);
 		if (bx < 1) bx = 1;
-		size_t s = begin_span(c);
+		SPAN_BEGIN(s);
 		peak_abs_kernel<<<dim3(bx, (unsigned) c->fmt.channels), 256, 0, c->stream>>>(c->d_y, c->y_pitch,
 		                                                                            c->fmt.frames, d_tmp);
-		end_span(c, s);
+		SPAN_END(s);
 		c->t_peak.push_back(s);
 		c->other_launches++;
 		CU_TRY(cudaGetLastError());
@@ -1078,13 +1148,40 @@ int fir_gpu_encode_dev(fir_gpu_ctx* c, double scale, void* pcm_dev)
 	DeviceGuard g(c->device);
 	if (c->fmt.frames == 0) return FIR_GPU_OK;
 	const double gain = scale * std::ldexp(1.0, c->fmt.bits - 1);
-	size_t s = begin_span(c);
-	DISPATCH_CODEC(launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->d_y, c->y_pitch, c->fmt.frames,
-	               c->fmt.channels, gain, (unsigned char*) pcm_dev);
-	end_span(c, s);
+	int rc = FIR_GPU_OK;
+	SPAN_BEGIN(s);
+	DISPATCH_CODEC(rc, launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->stream, c->d_y, c->y_pitch,
+	               c->fmt.frames, c->fmt.channels, gain, (unsigned char*) pcm_dev);
+	if (rc) return rc;
+	SPAN_END(s);
 	c->t_encode.push_back(s);
-	c->other_launches++;
-	CU_TRY(cudaGetLastError());
+	return FIR_GPU_OK;
+}
+
+// Encode frames [first, first+frames) of the parked signal into the staging buffer and bring
+// them to the host, on the high-priority output stream (ordered after the context's stream):
+// when another context's FIR fills the GPU, this file's way out does not wait behind it.
+static int encode_to_host(fir_gpu_ctx* c, double scale, int64_t first_frame, int64_t frames, void* pcm_host)
+{
+	const size_t fb = (size_t) c->fmt.channels * (c->fmt.bits / 8);
+	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, (size_t) c->fmt.frames * fb + 32);
+	if (rc) return rc;
+	if (frames == 0) return FIR_GPU_OK;
+	unsigned char* dst = c->d_pcm + (size_t) first_frame * fb;
+	const double gain = scale * std::ldexp(1.0, c->fmt.bits - 1);
+	CU_TRY(cudaEventRecord(c->enc_ready, c->stream));
+	CU_TRY(cudaStreamWaitEvent(c->d2h_stream, c->enc_ready, 0));
+	SPAN_BEGIN(se, c->d2h_stream);
+	DISPATCH_CODEC(rc, launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->d2h_stream, c->d_y + first_frame,
+	               c->y_pitch, frames, c->fmt.channels, gain, dst);
+	if (rc) return rc;
+	SPAN_END(se, c->d2h_stream);
+	c->t_encode.push_back(se);
+	SPAN_BEGIN(sc, c->d2h_stream);
+	CU_TRY(cudaMemcpyAsync(pcm_host, dst, (size_t) frames * fb, cudaMemcpyDeviceToHost, c->d2h_stream));
+	SPAN_END(sc, c->d2h_stream);
+	c->t_d2h.push_back(sc);
+	CU_TRY(cudaStreamSynchronize(c->d2h_stream));
 	return FIR_GPU_OK;
 }
 
@@ -1092,18 +1189,9 @@ int fir_gpu_encode(fir_gpu_ctx* c, double scale, void* pcm_host)
 {
 	if (!c || !pcm_host) return fail(FIR_GPU_ERR_INVALID, "null argument");
 	if (!c->parked || c->fmt.bits == 0) return fail(FIR_GPU_ERR_STATE, "no PCM-format signal is parked on this context");
+	if (!(scale > 0.0) || !std::isfinite(scale)) return fail(FIR_GPU_ERR_INVALID, "scale must be finite and > 0");
 	DeviceGuard g(c->device);
-	const size_t out_bytes = (size_t) c->fmt.frames * c->fmt.channels * (c->fmt.bits / 8);
-	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, out_bytes + 32);
-	if (rc) return rc;
-	rc = fir_gpu_encode_dev(c, scale, c->d_pcm);
-	if (rc) return rc;
-	size_t s = begin_span(c);
-	if (out_bytes) CU_TRY(cudaMemcpyAsync(pcm_host, c->d_pcm, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-	end_span(c, s);
-	c->t_d2h.push_back(s);
-	CU_TRY(cudaStreamSynchronize(c->stream));
-	return FIR_GPU_OK;
+	return encode_to_host(c, scale, 0, c->fmt.frames, pcm_host);
 }
 
 int fir_gpu_encode_range(fir_gpu_ctx* c, double scale, int64_t first_frame, int64_t frames, void* pcm_host)
@@ -1114,25 +1202,7 @@ int fir_gpu_encode_range(fir_gpu_ctx* c, double scale, int64_t first_frame, int6
 	if (first_frame < 0 || frames < 0 || first_frame + frames > c->fmt.frames || (first_frame & 1))
 		return fail(FIR_GPU_ERR_INVALID, "range must lie inside the parked signal and start on an even frame");
 	DeviceGuard g(c->device);
-	const size_t fb = (size_t) c->fmt.channels * (c->fmt.bits / 8);
-	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, (size_t) c->fmt.frames * fb + 32);
-	if (rc) return rc;
-	if (frames == 0) return FIR_GPU_OK;
-	unsigned char* dst = c->d_pcm + (size_t) first_frame * fb;
-	const double gain = scale * std::ldexp(1.0, c->fmt.bits - 1);
-	size_t s = begin_span(c);
-	DISPATCH_CODEC(launch_encode, c->fmt.bits, c->fmt.big_endian != 0, c, c->d_y + first_frame, c->y_pitch, frames,
-	               c->fmt.channels, gain, dst);
-	end_span(c, s);
-	c->t_encode.push_back(s);
-	c->other_launches++;
-	CU_TRY(cudaGetLastError());
-	s = begin_span(c);
-	CU_TRY(cudaMemcpyAsync(pcm_host, dst, (size_t) frames * fb, cudaMemcpyDeviceToHost, c->stream));
-	end_span(c, s);
-	c->t_d2h.push_back(s);
-	CU_TRY(cudaStreamSynchronize(c->stream));
-	return FIR_GPU_OK;
+	return encode_to_host(c, scale, first_frame, frames, pcm_host);
 }
 
 // ------------------------------------------------- measurement and synthesis
@@ -1142,6 +1212,7 @@ int fir_gpu_last_timing(fir_gpu_ctx* c, fir_gpu_timing* t)
 	if (!c || !t) return fail(FIR_GPU_ERR_INVALID, "null argument");
 	DeviceGuard g(c->device);
 	CU_TRY(cudaStreamSynchronize(c->stream));
+	CU_TRY(cudaStreamSynchronize(c->d2h_stream));
 	t->h2d_ms = span_ms(c, c->t_h2d);
 	t->decode_ms = span_ms(c, c->t_decode);
 	t->fir_ms = span_ms(c, c->t_fir);
@@ -1166,6 +1237,48 @@ int fir_gpu_synth_pcm_dev(fir_gpu_ctx* c, uint64_t seed, int64_t first_frame, in
 	synth_pcm_kernel<<<blocks, 256, 0, c->stream>>>(seed, first_frame, frames, channels, bits, big_endian, rate, gain,
 	                                               (unsigned char*) pcm_dev);
 	CU_TRY(cudaGetLastError());
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_copy_probe(fir_gpu_ctx* c, void* host_buf, size_t bytes, int dir, double* ms)
+{
+	if (!c || !host_buf || !ms) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	if (dir != 0 && dir != 1) return fail(FIR_GPU_ERR_INVALID, "dir must be 0 (H2D) or 1 (D2H)");
+	DeviceGuard g(c->device);
+	int rc = ensure((void**) &c->d_pcm, &c->pcm_cap, bytes + 32);
+	if (rc) return rc;
+	cudaEvent_t a, b;
+	CU_TRY(cudaEventCreate(&a));
+	cudaError_t e = cudaEventCreate(&b);
+	if (e == cudaSuccess) e = cudaEventRecord(a, c->stream);
+	if (e == cudaSuccess)
+		e = dir == 0 ? cudaMemcpyAsync(c->d_pcm, host_buf, bytes, cudaMemcpyHostToDevice, c->stream)
+		             : cudaMemcpyAsync(host_buf, c->d_pcm, bytes, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaEventRecord(b, c->stream);
+	if (e == cudaSuccess) e = cudaEventSynchronize(b);
+	float f = 0.f;
+	if (e == cudaSuccess) e = cudaEventElapsedTime(&f, a, b);
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	CU_TRY(e);
+	*ms = (double) f;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_set_codec_geometry(fir_gpu_ctx* c, int tile_bytes, int threads)
+{
+	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
+	if (threads != 128 && threads != 256) return fail(FIR_GPU_ERR_INVALID, "codec threads must be 128 or 256");
+	if (tile_bytes < 4096 || tile_bytes > 65536 - 4096)
+		return fail(FIR_GPU_ERR_INVALID, "codec tile must be 4 KiB .. 60 KiB");
+	c->codec_tile_bytes = tile_bytes;
+	c->codec_nt = threads;
+	return FIR_GPU_OK;
+}
+
+int fir_gpu_test_fail_next_create(int n)
+{
+	fir_gpu_test_fail_create.store(n < 0 ? 0 : n);
 	return FIR_GPU_OK;
 }
 

@@ -15,15 +15,42 @@
 
 namespace firgpu {
 
-constexpr int CODEC_NT = 256;
-constexpr int CODEC_TILE_BYTES = 32768; // interleaved bytes staged per CTA
+constexpr int CODEC_NT = 256;           // default threads per CTA (128 and 256 are supported)
+constexpr int CODEC_TILE_BYTES = 16384; // default interleaved bytes staged per tile
+constexpr int CODEC_SMEM_MAX = 72 * 1024;
+constexpr int CODEC_UNROLL = 4;         // independent 128-bit global loads a thread keeps in flight
 
-// frames per CTA tile for a frame of `fb` bytes: a multiple of 32 so a warp
-// never straddles two channels in the planar pass.
-__host__ __device__ inline int codec_tile_frames(int fb)
+// Geometry of one launch.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x, ...
+// Frames per tile are a multiple of 2*nt when the frame is narrow enough, so that in the planar
+// pass a "row" (nt threads x 2 consecutive frames) never straddles two channels and rows can be
+// unrolled with their loads issued back to back; otherwise a multiple of 32 (generic loop).
+struct CodecGeom {
+	int frames;      // frames per tile
+	int nt;          // threads per CTA
+	unsigned smem;   // dynamic shared memory per CTA
+	int ctas_per_sm; // resident CTAs per SM this geometry allows (grid = SMs x this, at most)
+};
+
+__host__ __device__ inline uint32_t pad_byte(uint32_t b);
+
+__host__ inline CodecGeom codec_geom(int fb, int tile_bytes = CODEC_TILE_BYTES, int nt = CODEC_NT)
 {
-	int f = (CODEC_TILE_BYTES / fb) & ~31;
-	return f < 32 ? 32 : f;
+	CodecGeom g;
+	int f = tile_bytes / fb;
+	if (f < 2 * nt && nt > 128 && f >= 256) nt = 128; // wide frames: rows of 128 thread-pairs still fit
+	g.nt = nt;
+	if (f >= 2 * nt) f = f / (2 * nt) * (2 * nt);
+	else {
+		f &= ~31;
+		if (f < 32) f = 32;
+	}
+	g.frames = f;
+	g.smem = pad_byte((uint32_t) (f * fb) + 64u) + 16u;
+	int by_smem = (int) ((227u * 1024u) / (g.smem + 1024u)), by_threads = 2048 / nt;
+	g.ctas_per_sm = by_smem < by_threads ? by_smem : by_threads;
+	if (g.ctas_per_sm > 32) g.ctas_per_sm = 32;
+	if (g.ctas_per_sm < 1) g.ctas_per_sm = 1;
+	return g;
 }
 
 // The shared tile keeps the interleaved bytes in a SKEWED layout: one pad word after
@@ -33,10 +60,6 @@ __host__ __device__ inline int codec_tile_frames(int fb)
 // conflict-free, and so are the four word stores of a 16-byte chunk per lane.
 __host__ __device__ inline uint32_t pad_word(uint32_t w) { return w + (w >> 5); }
 __host__ __device__ inline uint32_t pad_byte(uint32_t b) { return b + ((b >> 7) << 2); }
-__host__ __device__ inline size_t codec_smem_bytes(int tile_bytes)
-{
-	return (size_t) pad_byte((uint32_t) tile_bytes + 64u) + 16u;
-}
 
 // 4 bytes at an arbitrary byte offset of the skewed tile, packed little-endian
 // (byte at `off` in bits 0..7).
@@ -109,128 +132,200 @@ __device__ __forceinline__ void store_pcm_bytes(unsigned char* tile, uint32_t b,
 //   g0             : logical frame that lands at x index 0  (= first output frame - H)
 //   n_x            : x entries to write per channel (the whole pitch: zeros
 //                    wherever the logical frame is not available)
+//   F              : frames per tile (CodecGeom::frames)
+// Persistent CTAs: tile = blockIdx.x, +gridDim.x, ...  Per tile: FILL (interleaved bytes ->
+// skewed shared tile, CODEC_UNROLL independent LDG.128 per thread in flight), then the PLANAR
+// pass (two consecutive frames of one channel per thread -> one STG.128).
 template <int BITS, bool BE>
-__global__ void __launch_bounds__(CODEC_NT)
+__global__ void __launch_bounds__(256)
 pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, long long avail_hi,
-                  long long g0, long long n_x, int channels, double* __restrict__ x, long long x_pitch)
+                  long long g0, long long n_x, int channels, double* __restrict__ x, long long x_pitch, int F)
 {
 	constexpr int NB = BITS / 8;
+	constexpr int U = CODEC_UNROLL;
 	extern __shared__ __align__(16) unsigned char tile[];
+	const int nt = blockDim.x, tid = threadIdx.x;
 	const int fb = channels * NB;
-	const int F = codec_tile_frames(fb);
-	const long long i0 = (long long) blockIdx.x * F;
-
-	// logical frames of this tile that exist in pcm
-	long long ga = g0 + i0, gb = ga + F;
-	if (gb > g0 + n_x) gb = g0 + n_x;
-	if (ga < avail_lo) ga = avail_lo;
-	if (gb > avail_hi) gb = avail_hi;
-	uint32_t mis = 0;
-	if (gb > ga) {
-		const unsigned char* p0 = pcm + (size_t) (ga - avail_lo) * fb;
-		const uint32_t nbytes = (uint32_t) (gb - ga) * fb;
-		mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
-		const unsigned char* base = p0 - mis; // 16-byte aligned
-		const uint32_t end = mis + nbytes;
-		const uint32_t nvec = (end + 15u) >> 4;
-		for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
-			const uint32_t lo = v << 4, hi = lo + 16;
-			if (lo >= mis && hi <= end) {
-				const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + lo)); // 128-bit coalesced
-				uint32_t* d = reinterpret_cast<uint32_t*>(tile) + pad_word(v << 2);
-				d[0] = q.x;
-				d[1] = q.y;
-				d[2] = q.z;
-				d[3] = q.w;
-			} else { // ragged head / tail: never touch bytes outside the payload
-				const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
-				for (uint32_t s = lo; s < hi; ++s) tile[pad_byte(s)] = (s >= a && s < b) ? base[s] : 0;
-			}
-		}
-	}
-	__syncthreads();
-
+	const long long n_tiles = (n_x + F - 1) / F;
 	const double inv = 1.0 / (double) (1ll << (BITS - 1));
 	const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-	// Planar pass: channel by channel, a thread converts two consecutive frames and
-	// stores them with one 128-bit write (i0 and x_pitch are even, so the pair is
-	// 16-byte aligned).  No division in the loop.
-	const int la = (int) (ga - g0 - i0), lb = (int) (gb - g0 - i0); // tile-local frames present in pcm
-	int nloc = F;
-	if (i0 + nloc > n_x) nloc = (int) (n_x - i0);
-	for (int c = 0; c < channels; ++c) {
-		double* xc = x + (long long) c * x_pitch + i0;
-		const uint32_t cbase = mis + (uint32_t) c * NB - (uint32_t) la * fb;
-		for (int fl = 2 * threadIdx.x; fl < nloc; fl += 2 * CODEC_NT) {
-			double v0 = 0.0, v1 = 0.0;
-			if (fl >= la && fl < lb)
-				v0 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) fl * fb)) * inv;
-			if (fl + 1 >= la && fl + 1 < lb)
-				v1 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) (fl + 1) * fb)) * inv;
-			if (fl + 1 < nloc) *reinterpret_cast<double2*>(xc + fl) = make_double2(v0, v1);
-			else xc[fl] = v0;
+	const bool rows_ok = (F % (2 * nt)) == 0;
+
+	for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+		const long long i0 = tl * F;
+		// logical frames of this tile that exist in pcm
+		long long ga = g0 + i0, gb = ga + F;
+		if (gb > g0 + n_x) gb = g0 + n_x;
+		if (ga < avail_lo) ga = avail_lo;
+		if (gb > avail_hi) gb = avail_hi;
+		uint32_t mis = 0;
+		if (gb > ga) {
+			const unsigned char* p0 = pcm + (size_t) (ga - avail_lo) * fb;
+			const uint32_t nbytes = (uint32_t) (gb - ga) * fb;
+			mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
+			const unsigned char* base = p0 - mis; // 16-byte aligned
+			const uint32_t end = mis + nbytes;
+			const uint32_t nvec = (end + 15u) >> 4;
+			for (uint32_t v0 = tid; v0 < nvec; v0 += U * nt) {
+				uint4 q[U];
+				bool full[U];
+#pragma unroll
+				for (int k = 0; k < U; ++k) { // all the loads first: U x 16 B in flight per thread
+					const uint32_t v = v0 + k * nt, lo = v << 4;
+					full[k] = v < nvec && lo >= mis && lo + 16 <= end;
+					if (full[k]) q[k] = __ldg(reinterpret_cast<const uint4*>(base + lo)); // 128-bit coalesced
+				}
+#pragma unroll
+				for (int k = 0; k < U; ++k) {
+					const uint32_t v = v0 + k * nt, lo = v << 4, hi = lo + 16;
+					if (full[k]) {
+						uint32_t* d = reinterpret_cast<uint32_t*>(tile) + pad_word(v << 2);
+						d[0] = q[k].x;
+						d[1] = q[k].y;
+						d[2] = q[k].z;
+						d[3] = q[k].w;
+					} else if (v < nvec) { // ragged head / tail: never touch bytes outside the payload
+						const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
+						for (uint32_t s = lo; s < hi; ++s) tile[pad_byte(s)] = (s >= a && s < b) ? base[s] : 0;
+					}
+				}
+			}
 		}
+		__syncthreads();
+
+		const int la = (int) (ga - g0 - i0), lb = (int) (gb - g0 - i0); // tile-local frames present in pcm
+		int nloc = F;
+		if (i0 + nloc > n_x) nloc = (int) (n_x - i0);
+		if (rows_ok && nloc == F && la == 0 && lb == F) {
+			// whole tile, all of it real data: rows of nt thread-pairs, no per-sample predicates
+			const int rows_per_ch = F / (2 * nt), rows = channels * rows_per_ch;
+#pragma unroll 2
+			for (int r = 0; r < rows; ++r) {
+				const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
+				const uint32_t o = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
+				const double v0 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, o)) * inv;
+				const double v1 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, o + fb)) * inv;
+				*reinterpret_cast<double2*>(x + (long long) c * x_pitch + i0 + fl) = make_double2(v0, v1);
+			}
+		} else {
+			// edge tiles (zero padding, ragged end) and very wide frames: channel by channel, a thread
+			// converts two consecutive frames and stores them with one 128-bit write (i0 and x_pitch
+			// are even, so the pair is 16-byte aligned)
+			for (int c = 0; c < channels; ++c) {
+				double* xc = x + (long long) c * x_pitch + i0;
+				const uint32_t cbase = mis + (uint32_t) c * NB - (uint32_t) la * fb;
+				for (int fl = 2 * tid; fl < nloc; fl += 2 * nt) {
+					double v0 = 0.0, v1 = 0.0;
+					if (fl >= la && fl < lb)
+						v0 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) fl * fb)) * inv;
+					if (fl + 1 >= la && fl + 1 < lb)
+						v1 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, cbase + (uint32_t) (fl + 1) * fb)) * inv;
+					if (fl + 1 < nloc) *reinterpret_cast<double2*>(xc + fl) = make_double2(v0, v1);
+					else xc[fl] = v0;
+				}
+			}
+		}
+		__syncthreads(); // the tile is refilled by the next trip
 	}
 }
 
 // Planar FP64 -> interleaved PCM.  gain = scale * 2^(bits-1) (one rounding, on
 // the host); the product y*gain is rounded to binary64, then to the nearest
 // integer with ties to even (cvt.rni), after clamping to the signed range.
+// Persistent CTAs like the decoder.  Per tile: the PLANAR pass (CODEC_UNROLL independent
+// LDG.128 of the parked signal in flight per thread, then quantise and drop the bytes into
+// the skewed tile), then the DRAIN (128-bit coalesced stores of the interleaved bytes).
 template <int BITS, bool BE>
-__global__ void __launch_bounds__(CODEC_NT)
+__device__ __forceinline__ uint32_t quantise(double v, double gain, double lo_lim, double hi_lim)
+{
+	v = fmin(fmax(v * gain, lo_lim), hi_lim);
+	return int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v));
+}
+
+template <int BITS, bool BE>
+__global__ void __launch_bounds__(256)
 pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long frames, int channels,
-                  double gain, unsigned char* __restrict__ pcm)
+                  double gain, unsigned char* __restrict__ pcm, int F)
 {
 	constexpr int NB = BITS / 8;
+	constexpr int U = CODEC_UNROLL;
 	extern __shared__ __align__(16) unsigned char tile[];
+	const int nt = blockDim.x, tid = threadIdx.x;
 	const int fb = channels * NB;
-	const int F = codec_tile_frames(fb);
-	const long long f0 = (long long) blockIdx.x * F;
-	long long f1 = f0 + F;
-	if (f1 > frames) f1 = frames;
-	const int nf = (int) (f1 - f0);
-
-	unsigned char* p0 = pcm + (size_t) f0 * fb;
-	const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
+	const long long n_tiles = (frames + F - 1) / F;
 	const double hi_lim = (double) ((1ll << (BITS - 1)) - 1), lo_lim = -(double) (1ll << (BITS - 1));
+	const bool rows_ok = (F % (2 * nt)) == 0;
 
-	// Planar pass: channel by channel, a thread quantises two consecutive frames
-	// (one 128-bit load when both exist) and drops their bytes into the tile.
-	for (int c = 0; c < channels; ++c) {
-		const double* yc = y + (long long) c * y_pitch + f0;
-		const uint32_t dc = mis + (uint32_t) c * NB;
-		for (int fl = 2 * threadIdx.x; fl < nf; fl += 2 * CODEC_NT) {
-			double v0, v1 = 0.0;
-			const bool two = fl + 1 < nf;
-			if (two) {
-				const double2 v = *reinterpret_cast<const double2*>(yc + fl);
-				v0 = v.x;
-				v1 = v.y;
-			} else {
-				v0 = yc[fl];
+	for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+		const long long f0 = tl * F;
+		long long f1 = f0 + F;
+		if (f1 > frames) f1 = frames;
+		const int nf = (int) (f1 - f0);
+		unsigned char* p0 = pcm + (size_t) f0 * fb;
+		const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
+
+		if (rows_ok && nf == F) {
+			const int rows_per_ch = F / (2 * nt), rows = channels * rows_per_ch;
+			for (int r0 = 0; r0 < rows; r0 += U) {
+				double2 v[U];
+#pragma unroll
+				for (int k = 0; k < U; ++k) { // all the loads first
+					const int r = r0 + k;
+					if (r < rows) {
+						const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
+						v[k] = __ldg(reinterpret_cast<const double2*>(y + (long long) c * y_pitch + f0 + fl));
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < U; ++k) {
+					const int r = r0 + k;
+					if (r < rows) {
+						const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
+						const uint32_t o = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
+						store_pcm_bytes<NB>(tile, o, quantise<BITS, BE>(v[k].x, gain, lo_lim, hi_lim));
+						store_pcm_bytes<NB>(tile, o + fb, quantise<BITS, BE>(v[k].y, gain, lo_lim, hi_lim));
+					}
+				}
 			}
-			v0 = fmin(fmax(v0 * gain, lo_lim), hi_lim);
-			v1 = fmin(fmax(v1 * gain, lo_lim), hi_lim);
-			store_pcm_bytes<NB>(tile, dc + (uint32_t) fl * fb, int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v0)));
-			if (two)
-				store_pcm_bytes<NB>(tile, dc + (uint32_t) (fl + 1) * fb,
-				                    int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v1)));
-		}
-	}
-	__syncthreads();
-
-	unsigned char* base = p0 - mis;
-	const uint32_t end = mis + (uint32_t) nf * fb;
-	const uint32_t nvec = (end + 15u) >> 4;
-	for (uint32_t v = threadIdx.x; v < nvec; v += CODEC_NT) {
-		const uint32_t lo = v << 4, hi = lo + 16;
-		if (lo >= mis && hi <= end) {
-			const uint32_t* q = reinterpret_cast<const uint32_t*>(tile) + pad_word(v << 2);
-			*reinterpret_cast<uint4*>(base + lo) = make_uint4(q[0], q[1], q[2], q[3]); // 128-bit coalesced
 		} else {
-			const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
-			for (uint32_t s = a; s < b; ++s) base[s] = tile[pad_byte(s)];
+			// ragged last tile and very wide frames: channel by channel, two consecutive frames per
+			// thread (one 128-bit load when both exist)
+			for (int c = 0; c < channels; ++c) {
+				const double* yc = y + (long long) c * y_pitch + f0;
+				const uint32_t dc = mis + (uint32_t) c * NB;
+				for (int fl = 2 * tid; fl < nf; fl += 2 * nt) {
+					double v0, v1 = 0.0;
+					const bool two = fl + 1 < nf;
+					if (two) {
+						const double2 v = *reinterpret_cast<const double2*>(yc + fl);
+						v0 = v.x;
+						v1 = v.y;
+					} else {
+						v0 = yc[fl];
+					}
+					store_pcm_bytes<NB>(tile, dc + (uint32_t) fl * fb, quantise<BITS, BE>(v0, gain, lo_lim, hi_lim));
+					if (two)
+						store_pcm_bytes<NB>(tile, dc + (uint32_t) (fl + 1) * fb,
+						                    quantise<BITS, BE>(v1, gain, lo_lim, hi_lim));
+				}
+			}
 		}
+		__syncthreads();
+
+		unsigned char* base = p0 - mis;
+		const uint32_t end = mis + (uint32_t) nf * fb;
+		const uint32_t nvec = (end + 15u) >> 4;
+		for (uint32_t v = tid; v < nvec; v += nt) {
+			const uint32_t lo = v << 4, hi = lo + 16;
+			if (lo >= mis && hi <= end) {
+				const uint32_t* q = reinterpret_cast<const uint32_t*>(tile) + pad_word(v << 2);
+				*reinterpret_cast<uint4*>(base + lo) = make_uint4(q[0], q[1], q[2], q[3]); // 128-bit coalesced
+			} else {
+				const uint32_t a = lo > mis ? lo : mis, b = hi < end ? hi : end;
+				for (uint32_t s = a; s < b; ++s) base[s] = tile[pad_byte(s)];
+			}
+		}
+		__syncthreads(); // the tile is rewritten by the next trip
 	}
 }
 

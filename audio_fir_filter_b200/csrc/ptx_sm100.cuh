@@ -48,9 +48,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 	return ok != 0;
 }
 
+// try_wait itself blocks for a hardware-defined slice before it reports failure, so a healthy
+// wait sees a handful of failures at most.  A bulk copy that faulted never completes its
+// transaction count: after MBAR_SPIN_LIMIT failed slices (seconds) the kernel traps, which the
+// host sees as a CUDA error (FIR_GPU_ERR_CUDA) instead of a hang.
+constexpr uint32_t MBAR_SPIN_LIMIT = 1u << 24;
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-	while (!mbar_try_wait(bar, parity)) {}
+	uint32_t spins = 0;
+	while (!mbar_try_wait(bar, parity)) {
+		if (++spins > MBAR_SPIN_LIMIT) __trap();
+	}
 }
 
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`.

@@ -68,9 +68,14 @@ double extended80_to_double(const unsigned char* p)
 	return sign ? -v : v;
 }
 
+UniqueFd::~UniqueFd()
+{
+	if (fd >= 0) ::close(fd);
+}
+
 AudioContainer::AudioContainer(const std::filesystem::path& path) : path_(path)
 {
-	fd_ = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+	fd_.fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
 	if (fd_ < 0) throw FileNotFound(path.string());
 	struct stat st{};
 	if (::fstat(fd_, &st) != 0) throw FormatError("cannot stat " + path.string());
@@ -91,16 +96,12 @@ AudioContainer::AudioContainer(const std::filesystem::path& path) : path_(path)
 	if (pcm_.payload_offset == 0) throw FormatError(path.string() + ": no sample chunk");
 	if (pcm_.payload_offset > size_) throw FormatError(path.string() + ": the sample chunk starts beyond the end of the file");
 	const uint64_t fb = (uint64_t) pcm_.channels * (pcm_.bits / 8);
-	// a truncated file keeps what is there; partial trailing frames are not samples
-	if (pcm_.payload_offset + pcm_.payload_bytes > size_)
-		pcm_.payload_bytes = size_ > pcm_.payload_offset ? size_ - pcm_.payload_offset : 0;
+	// a truncated file keeps what is there; partial trailing frames are not samples.  Sizes come
+	// from the file (an RF64 ds64 size can be anything up to 2^64): compare by subtraction, a sum
+	// could wrap and slip past the clamp
+	pcm_.payload_bytes = std::min(pcm_.payload_bytes, size_ - pcm_.payload_offset);
 	pcm_.frames = pcm_.payload_bytes / fb;
 	pcm_.payload_bytes = pcm_.frames * fb;
-}
-
-AudioContainer::~AudioContainer()
-{
-	if (fd_ >= 0) ::close(fd_);
 }
 
 const char* AudioContainer::type_name() const
@@ -132,6 +133,11 @@ void AudioContainer::parse_riff()
 			have_ds64 = true;
 		}
 		if (!std::memcmp(c.id, "data", 4) && c.size == 0xFFFFFFFFu && have_ds64) c.size = ds64_data;
+		// a chunk cannot reach beyond the end of the file (truncated file, hostile ds64 size): it
+		// ends where the file ends, and the walk stops there instead of wrapping around
+		const uint64_t room = size_ - c.data_offset; // pos + 8 <= size_
+		const bool truncated = c.size > room;
+		if (truncated) c.size = room;
 		if (!std::memcmp(c.id, "fmt ", 4)) {
 			unsigned char f[40] = {};
 			const uint64_t n = std::min<uint64_t>(c.size, 40);
@@ -154,9 +160,8 @@ void AudioContainer::parse_riff()
 			pcm_.payload_bytes = c.size;
 		}
 		chunks_.push_back(c);
-		const uint64_t next = c.data_offset + c.size + (c.size & 1);
-		if (next <= pos) break;
-		pos = next;
+		if (truncated) break;
+		pos = c.data_offset + c.size + (c.size & 1); // <= size_ + 1: cannot wrap
 	}
 }
 
@@ -172,6 +177,9 @@ void AudioContainer::parse_iff()
 		c.header_offset = pos;
 		c.data_offset = pos + 8;
 		c.size = be32(h + 4);
+		const uint64_t room = size_ - c.data_offset; // pos + 8 <= size_
+		const bool truncated = c.size > room;
+		if (truncated) c.size = room;
 		if (!std::memcmp(c.id, "COMM", 4)) {
 			unsigned char f[22] = {};
 			const uint64_t n = std::min<uint64_t>(c.size, 22);
@@ -192,17 +200,17 @@ void AudioContainer::parse_iff()
 			if (pcm_.channels < 1) throw FormatError(path_.string() + ": bad COMM chunk");
 			pcm_.bits = container_bits(pcm_.valid_bits, (pcm_.valid_bits + 7) / 8, path_.string());
 		}
-		if (!std::memcmp(c.id, "SSND", 4) && ssnd_data == 0 && c.size >= 8 && c.data_offset + 8 <= size_) {
+		if (!std::memcmp(c.id, "SSND", 4) && ssnd_data == 0 && c.size >= 8) {
 			unsigned char f[8];
 			pread_all(fd_, f, 8, c.data_offset, path_.string());
 			const uint64_t offset = be32(f); // + blockSize at f+4: alignment hint only
+			if (offset > c.size - 8) throw FormatError(path_.string() + ": SSND offset lies beyond its chunk");
 			ssnd_data = c.data_offset + 8 + offset;
-			ssnd_size = c.size >= 8 + offset ? c.size - 8 - offset : 0;
+			ssnd_size = c.size - 8 - offset;
 		}
 		chunks_.push_back(c);
-		const uint64_t next = c.data_offset + c.size + (c.size & 1);
-		if (next <= pos) break;
-		pos = next;
+		if (truncated) break;
+		pos = c.data_offset + c.size + (c.size & 1); // <= size_ + 1: cannot wrap
 	}
 	if (ssnd_data && pcm_.channels > 0) { // COMM may come after SSND
 		pcm_.payload_offset = ssnd_data;
@@ -220,7 +228,7 @@ void AudioContainer::advise_willneed() const
 
 void AudioContainer::read_payload(uint64_t offset, uint64_t n, void* dst) const
 {
-	if (offset + n > pcm_.payload_bytes) throw FormatError("payload read out of range");
+	if (offset > pcm_.payload_bytes || n > pcm_.payload_bytes - offset) throw FormatError("payload read out of range");
 	pread_all(fd_, dst, n, pcm_.payload_offset + offset, path_.string());
 }
 
@@ -250,7 +258,7 @@ int AudioContainer::create_output(const std::filesystem::path& out) const
 
 void AudioContainer::write_payload(int fd, const PcmLayout& pcm, uint64_t offset, uint64_t n, const void* src)
 {
-	if (offset + n > pcm.payload_bytes) throw FormatError("payload write out of range");
+	if (offset > pcm.payload_bytes || n > pcm.payload_bytes - offset) throw FormatError("payload write out of range");
 	pwrite_all(fd, src, n, pcm.payload_offset + offset);
 }
 

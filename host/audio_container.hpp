@@ -37,12 +37,24 @@ struct PcmLayout {
 	double sample_rate = 0.0;
 };
 
+// A file descriptor that is closed when its owner goes away -- including when the owner's
+// constructor throws half-way (a destructor does not run for a partially built object, the
+// destructors of its finished members do).
+struct UniqueFd {
+	int fd = -1;
+	UniqueFd() = default;
+	explicit UniqueFd(int f) : fd(f) {}
+	UniqueFd(const UniqueFd&) = delete;
+	UniqueFd& operator=(const UniqueFd&) = delete;
+	~UniqueFd();
+	operator int() const { return fd; }
+};
+
 class AudioContainer {
 public:
 	// Parses the chunk structure; throws FormatError on anything that is not
 	// integer PCM of 16/24/32 bits in a WAVE/RF64/AIFF/AIFF-C container.
 	explicit AudioContainer(const std::filesystem::path& path);
-	~AudioContainer();
 	AudioContainer(const AudioContainer&) = delete;
 	AudioContainer& operator=(const AudioContainer&) = delete;
 
@@ -68,7 +80,7 @@ private:
 	void parse_riff();
 	void parse_iff();
 	std::filesystem::path path_;
-	int fd_ = -1;
+	UniqueFd fd_;
 	uint64_t size_ = 0;
 	ContainerType type_ = ContainerType::Wave;
 	std::vector<ChunkInfo> chunks_;

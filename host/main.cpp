@@ -6,6 +6,7 @@
 #include <filesystem>
 #include <format>
 #include <iostream>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,7 +63,9 @@ int main(int argc, char** argv)
 			GpuPool pool(cli.gpus);
 			// main.cp:69-72 prints its resource line only when -v is NOT given; kept as is
 			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
-			if (fs::exists(out)) fs::remove(out);
+			// the reference removes an existing output up front (main.cp:107); here the result is
+			// written to <out>.part and renamed over the old file only once it is complete, so a
+			// failure leaves the old output in place
 			if (opts.verbose) std::cout << std::format("  [{:8.3f} s] devices counted", since_start()) << std::endl;
 			process_file(in, out, opts, pool);
 			if (opts.verbose) std::cout << std::format("  [{:8.3f} s] done", since_start()) << std::endl;
@@ -83,19 +86,32 @@ int main(int argc, char** argv)
 			// the reference validates each file as it reaches it (main.cp:132-147); the
 			// per-GPU workers run files concurrently, so validate them all up front
 			std::vector<std::pair<fs::path, fs::path>> jobs;
+			std::set<fs::path> claimed; // destinations of this run
 			for (size_t i = 0; i + 1 < paths.size(); ++i) {
 				const fs::path& in = paths[i];
 				if (!fs::exists(in) || !fs::is_regular_file(in)) throw FileNotFound(in.string());
 				fs::path out = dest / in.filename();
 				if (fs::exists(out) && fs::equivalent(in, out))
 					throw UsageError("Input and output are the same file: " + in.string());
+				// Two inputs with one basename (a/x.wav b/x.wav out/) map to one destination.  The
+				// reference runs files in sequence, so its second iteration finds the first one's
+				// output and stops with FileExists (main.cp:140-142) unless -O is given; with -O the
+				// later file wins.  Files run concurrently here, and two lanes writing one .part file
+				// would corrupt it, so the clash is settled before anything runs.
+				if (!claimed.insert(fs::weakly_canonical(out)).second) {
+					if (!cli.overwrite) throw FileExists(out.string());
+					for (auto& j : jobs)
+						if (fs::weakly_canonical(j.second) == fs::weakly_canonical(out)) j.first = in; // last one wins
+					continue;
+				}
 				if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
 				jobs.emplace_back(in, out);
 			}
 			GpuPool pool(cli.gpus);
 			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
-			for (const auto& j : jobs)
-				if (fs::exists(j.second)) fs::remove(j.second);
+			// existing destinations (-O) are replaced one by one, by the rename that completes each
+			// file (the reference removes each only when it reaches it, main.cp:144): if a file
+			// fails, the old outputs of the files that were not reached are still there
 			process_batch(jobs, opts, pool);
 			leave_now();
 		}

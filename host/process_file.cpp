@@ -117,6 +117,17 @@ void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContaine
 	const uint64_t fb = (uint64_t) l.channels * (l.bits / 8);
 	const fir_gpu_pcm fmt = make_fmt(l, b.frames, b.halo_l, b.halo_r);
 	BlockProgress bp{bar};
+	// `bp` is the user pointer of callbacks that the CUDA runtime runs later, from its own thread:
+	// whatever way this function is left (a short read, a failed call), the hook is removed and
+	// the stream drained before `bp` goes out of scope
+	struct HookGuard {
+		fir_gpu_ctx* ctx;
+		~HookGuard()
+		{
+			fir_gpu_set_progress(ctx, nullptr, nullptr);
+			fir_gpu_synchronize(ctx);
+		}
+	} unhook{ctx};
 	check(fir_gpu_set_progress(ctx, on_chunk_done, &bp), "fir_gpu_set_progress");
 	check(fir_gpu_apply_begin(ctx, k, &fmt), "fir_gpu_apply_begin");
 	const uint64_t first = (uint64_t) (b.start - b.halo_l) * fb, total = (uint64_t) (b.halo_l + b.frames + b.halo_r) * fb;
@@ -130,7 +141,6 @@ void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContaine
 	}
 	check(fir_gpu_apply_end(ctx), "fir_gpu_apply_end");
 	check(fir_gpu_peak(ctx, peak), "fir_gpu_peak");            // ProcessFile.cp:92-96; waits for the FIR
-	fir_gpu_set_progress(ctx, nullptr, nullptr);
 }
 
 // Encode the block with the common scale and write it into the output's sample chunk,

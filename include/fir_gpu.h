@@ -108,11 +108,6 @@ FIR_GPU_API void fir_gpu_host_free(void *p);
 FIR_GPU_API int fir_gpu_build_kernel(fir_gpu_ctx *ctx, double fc_norm, double bw_norm,
                                      fir_gpu_kernel **out, int64_t *half_len);
 
-/* A kernel from caller-supplied taps (n_taps odd): for parity tests that must
- * feed the device the oracle's exact taps. */
-FIR_GPU_API int fir_gpu_kernel_from_taps(fir_gpu_ctx *ctx, const double *taps, int64_t n_taps,
-                                         fir_gpu_kernel **out);
-
 FIR_GPU_API int64_t fir_gpu_kernel_num_taps(const fir_gpu_kernel *k);
 /* Copy the M+1 taps back to the host (parity checks). */
 FIR_GPU_API int fir_gpu_kernel_taps(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, double *taps_out,
@@ -206,27 +201,13 @@ FIR_GPU_API int fir_gpu_process(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const
                                 const fir_gpu_pcm *fmt, int normalize, void *pcm_out_host, double *peak,
                                 double *scale);
 
-/* ---- measurement & synthetic input --------------------------------------- */
+/* ---- per-phase device times ------------------------------------------------ */
 
 FIR_GPU_API int fir_gpu_last_timing(fir_gpu_ctx *ctx, fir_gpu_timing *t);
 
-/* Counter-based synthetic PCM (same integers as oracle_synth_pcm), written to
- * device memory: any window of any config without materialising the file. */
-FIR_GPU_API int fir_gpu_synth_pcm_dev(fir_gpu_ctx *ctx, uint64_t seed, int64_t first_frame,
-                                      int64_t frames, int32_t channels, int32_t bits,
-                                      int32_t big_endian, int64_t rate, double gain, void *pcm_dev);
-
-/* Register-resident FP64 throughput probes (TFLOP/s) used as the measured
- * roofline denominator: kind 0 = DFMA pipe, 1 = DMMA (mma.sync m8n8k4 f64). */
-FIR_GPU_API int fir_gpu_fp64_peak(fir_gpu_ctx *ctx, int kind, double seconds, double *tflops);
-
-/* Tuning knobs for experiments: FIR kernel variant (0 = default), and the bound
- * on the decoded FP64 input scratch (files longer than this stream through it
- * chunk by chunk; the result does not depend on it). */
-FIR_GPU_API int fir_gpu_set_variant(fir_gpu_ctx *ctx, int variant);
-FIR_GPU_API int fir_gpu_variant_count(void);
-FIR_GPU_API const char *fir_gpu_variant_name(int variant);
-FIR_GPU_API int fir_gpu_set_x_budget(fir_gpu_ctx *ctx, int64_t bytes);
+/* Measurement, synthetic-input and tuning entry points (probes, kernel variants,
+ * caller-supplied taps) are NOT part of the drop-in boundary: they are declared in
+ * fir_gpu_dev.h and used only by bench.py, tools/ and the tests. */
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,8 @@ import pytest
 from conftest import ROOT
 
 
-def header_symbols():
-    text = open(os.path.join(ROOT, "include", "fir_gpu.h")).read()
+def header_symbols(name="fir_gpu.h"):
+    text = open(os.path.join(ROOT, "include", name)).read()
     return re.findall(r"FIR_GPU_API\s+[\w\s\*]+?\b(fir_gpu_\w+)\s*\(", text)
 
 
@@ -20,6 +20,20 @@ def test_header_and_binding_agree():
     syms = header_symbols()
     assert len(syms) >= 25
     assert sorted(syms) == sorted(capi.SYMBOLS)
+    assert sorted(header_symbols("fir_gpu_dev.h")) == sorted(capi.DEV_SYMBOLS)
+    assert not set(capi.SYMBOLS) & set(capi.DEV_SYMBOLS)
+
+
+def test_boundary_header_carries_no_measurement_or_test_entry_points():
+    """Probes, synthetic input, kernel variants and test hooks live in fir_gpu_dev.h, which the
+    C++ host never includes."""
+    pub = header_symbols()
+    for s in ("fir_gpu_fp64_peak", "fir_gpu_set_variant", "fir_gpu_synth_pcm_dev", "fir_gpu_set_x_budget",
+              "fir_gpu_kernel_from_taps", "fir_gpu_copy_probe", "fir_gpu_test_fail_next_create"):
+        assert s not in pub, s
+    for f in os.listdir(os.path.join(ROOT, "host")):
+        if f.endswith((".cpp", ".hpp")):
+            assert "fir_gpu_dev.h" not in open(os.path.join(ROOT, "host", f)).read(), f
 
 
 def test_library_exports_every_declared_symbol():
@@ -27,7 +41,7 @@ def test_library_exports_every_declared_symbol():
 
     assert os.path.exists(capi.LIB_PATH), "libfir_gpu.so was not built (run __graft_entry__.build())"
     L = ctypes.CDLL(capi.LIB_PATH)
-    for s in header_symbols():
+    for s in header_symbols() + header_symbols("fir_gpu_dev.h"):
         assert hasattr(L, s), s
     assert capi.lib() is not None
 

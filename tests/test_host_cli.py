@@ -300,3 +300,92 @@ def test_cli_option_syntax_variants(tmp_path):
     assert r.returncode == 1 and "invalid" in r.stderr
     r = run("-f", "1e", missing, out)
     assert r.returncode == 1 and "invalid" in r.stderr
+
+
+def test_container_sizes_near_2_64_cannot_wrap_the_clamp(tmp_path):
+    """Chunk sizes come from the file.  An RF64 ds64 data size or an SSND offset near 2^64 / 2^32
+    must not wrap `offset + size` past the truncation clamp: the payload is what the
+    file holds, never more."""
+    import struct
+
+    pcm = rand_pcm(200, 2, 16)
+    good = wav_bytes(pcm, 2, 16, 44100, rf64=True, extra_before=False, extra_after=False)
+    at = good.index(b"ds64") + 8 + 8                       # the 64-bit data size inside ds64
+    for size in (2**64 - 1, 2**64 - 8, 2**64 - len(good), 2**63, 2**32 + 5):
+        b = bytearray(good)
+        b[at:at + 8] = struct.pack("<Q", size)
+        p = tmp_path / f"ds64_{size}.wav"
+        p.write_bytes(bytes(b))
+        i = info(p)
+        assert i["payload_offset"] + i["payload_bytes"] <= len(b)
+        assert i["frames"] == 200 and i["payload_bytes"] == len(pcm)      # clamped to what is there
+        r = subprocess.run([TOOL, "invert", str(p), str(tmp_path / "o.wav")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    aif = aiff_bytes(pcm, 2, 16, 44100.0, extra=False)
+    at = aif.index(b"SSND") + 8                            # SSND offset field
+    for off in (2**32 - 1, 2**32 - 8, len(aif), 2**31):
+        b = bytearray(aif)
+        b[at:at + 4] = struct.pack(">I", off)
+        p = tmp_path / f"ssnd_{off}.aif"
+        p.write_bytes(bytes(b))
+        r = subprocess.run([TOOL, "info", str(p)], capture_output=True, text=True)
+        assert r.returncode == 1 and "SSND offset" in r.stderr, (off, r.stdout, r.stderr)
+
+
+def test_container_constructor_does_not_leak_descriptors_on_format_errors(tmp_path):
+    """A FormatError thrown by the constructor must close the file again (the destructor of a
+    partially built object never runs).  lowcut opens every batch input up front, so a leak
+    here would be one descriptor per rejected file."""
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"RIFF\x04\0\0\0WAVE")                 # no fmt, no data
+    src = os.path.join(ROOT, "tests", "harness", "fd_leak_probe.cpp")
+    exe = tmp_path / "fd_leak_probe"
+    r = subprocess.run(["g++", "-std=c++23", "-O1", "-I", os.path.join(ROOT, "host"), "-o", str(exe), src,
+                        os.path.join(ROOT, "host", "audio_container.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(bad)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "leaked=0" in r.stdout, r.stdout
+
+
+def test_cli_batch_two_inputs_with_one_basename(tmp_path):
+    """a/x.wav b/x.wav out/ map to one destination.  The reference runs files one after the
+    other: its second iteration finds the first one's output and throws FileExists
+    (main.cp:140-142).  Files run concurrently here, so the clash is found up front -- before a
+    GPU is needed -- instead of two lanes corrupting one .part file."""
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    data = wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100)
+    (tmp_path / "a" / "x.wav").write_bytes(data)
+    (tmp_path / "b" / "x.wav").write_bytes(data)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = run(tmp_path / "a" / "x.wav", tmp_path / "b" / "x.wav", out)
+    assert r.returncode == 1 and "File exists" in r.stderr and "x.wav" in r.stderr
+    assert not list(out.iterdir())                         # nothing was started
+
+
+def test_cli_overwrite_keeps_old_outputs_until_each_file_is_done(tmp_path):
+    """-O no longer deletes every existing destination before the first file runs: the old file
+    is replaced by the rename that completes its successor (the reference removes each output
+    only when it reaches that file, main.cp:144).  Without a GPU the run fails -- and the old
+    outputs must still be there."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run would succeed")
+    a = tmp_path / "a.wav"
+    a.write_bytes(wav_bytes(rand_pcm(64, 2, 16), 2, 16, 44100))
+    b = tmp_path / "b.wav"
+    b.write_bytes(a.read_bytes())
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "a.wav").write_bytes(b"old a")
+    (out / "b.wav").write_bytes(b"old b")
+    r = run("-O", a, b, out)
+    assert r.returncode == 1
+    assert (out / "a.wav").read_bytes() == b"old a" and (out / "b.wav").read_bytes() == b"old b"
+    single = tmp_path / "single.wav"
+    single.write_bytes(b"old single")
+    r = run("-O", a, single)
+    assert r.returncode == 1 and single.read_bytes() == b"old single"
