@@ -14,7 +14,9 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfir_gpu.so")
+# FIR_GPU_LIB selects another build of the same library (tools/sweep_variants.py uses the
+# -DFIR_ALL_VARIANTS build, libfir_gpu_sweep.so); there is still no fallback of any kind.
+LIB_PATH = os.environ.get("FIR_GPU_LIB") or os.path.join(_PKG, "libfir_gpu.so")
 
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = range(6)
 _CODE_NAMES = {1: "NO_DEVICE", 2: "INVALID", 3: "CUDA", 4: "STATE", 5: "NOMEM"}
@@ -91,6 +93,8 @@ SYMBOLS = {
     "fir_gpu_peak": (C.c_int, [_vp, _dp]),
     "fir_gpu_peak_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
     "fir_gpu_peak_recompute": (C.c_int, [_vp, _dp]),
+    "fir_gpu_comm_prepare": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "fir_gpu_allreduce_peak": (C.c_int, [C.POINTER(_vp), C.c_int, _dp]),
     "fir_gpu_encode": (C.c_int, [_vp, C.c_double, _vp]),
     "fir_gpu_encode_dev": (C.c_int, [_vp, C.c_double, _vp]),
     "fir_gpu_last_timing": (C.c_int, [_vp, C.POINTER(Timing)]),
@@ -102,6 +106,7 @@ DEV_SYMBOLS = {
                                         _i64, C.c_double, _vp]),
     "fir_gpu_fp64_peak": (C.c_int, [_vp, C.c_int, C.c_double, _dp]),
     "fir_gpu_copy_probe": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _dp]),
+    "fir_gpu_reserve": (C.c_int, [_vp, _vp, C.POINTER(PcmFormat), C.c_int]),
     "fir_gpu_set_variant": (C.c_int, [_vp, C.c_int]),
     "fir_gpu_variant_count": (C.c_int, []),
     "fir_gpu_variant_name": (C.c_char_p, [C.c_int]),
@@ -356,6 +361,11 @@ class Context:
         _check(lib().fir_gpu_copy_probe(self._h, _ptr(host_buf), nbytes, direction, C.byref(v)))
         return float(v.value)
 
+    def reserve(self, kernel: Kernel, frames: int, channels: int, bits: int, big_endian: bool, halo_left: int = 0,
+                halo_right: int = 0, host_path: bool = False) -> None:
+        fmt = self._fmt(frames, channels, bits, big_endian, halo_left, halo_right)
+        _check(lib().fir_gpu_reserve(self._h, kernel._h, C.byref(fmt), int(host_path)))
+
     def set_codec_geometry(self, tile_bytes: int, threads: int) -> None:
         _check(lib().fir_gpu_set_codec_geometry(self._h, tile_bytes, threads))
 
@@ -364,6 +374,20 @@ class Context:
 
     def set_x_budget(self, nbytes: int) -> None:
         _check(lib().fir_gpu_set_x_budget(self._h, nbytes))
+
+
+def allreduce_peak(ctxs: list[Context]) -> float:
+    """fir_gpu_allreduce_peak: ONE ncclAllReduce(max) over the peak scalars of contexts on distinct
+    devices of this process (sample-block mode); every context then holds the global peak."""
+    arr = (_vp * len(ctxs))(*[c._h for c in ctxs])
+    v = C.c_double()
+    _check(lib().fir_gpu_allreduce_peak(arr, len(ctxs), C.byref(v)))
+    return float(v.value)
+
+
+def comm_prepare(ctxs: list[Context]) -> None:
+    arr = (_vp * len(ctxs))(*[c._h for c in ctxs])
+    _check(lib().fir_gpu_comm_prepare(arr, len(ctxs)))
 
 
 def variant_names() -> list[str]:

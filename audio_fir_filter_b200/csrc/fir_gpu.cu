@@ -18,13 +18,16 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -208,7 +211,11 @@ struct fir_gpu_ctx {
 	int64_t fir_launches = 0, other_launches = 0;
 	int64_t x_budget_bytes = (int64_t) 2 << 30;
 	// cudaFuncSetAttribute is per device: remember what this context's device has
-	bool codec_attr[12] = {};
+	struct CodecSlot {
+		bool attr_done = false;
+		int nt = 0, resident = 0;
+		unsigned smem = 0;
+	} codec_slot[12];
 	int codec_tile_bytes = CODEC_TILE_BYTES, codec_nt = CODEC_NT;
 	std::vector<char> fir_attr;
 };
@@ -336,20 +343,39 @@ int check_fmt(const fir_gpu_pcm* f)
 	return FIR_GPU_OK;
 }
 
+// CTAs of a codec kernel that are resident per SM at this geometry -- asked of the runtime, not
+// estimated: the persistent grid must be exactly one wave (a CTA that does not fit starts when
+// another finishes, i.e. at the very end, and runs its share of the tiles almost alone).
+int codec_residency(fir_gpu_ctx* c, int slot, const void* fn, const CodecGeom& g, int* resident)
+{
+	fir_gpu_ctx::CodecSlot& s = c->codec_slot[slot];
+	if (!s.attr_done) {
+		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, CODEC_SMEM_MAX));
+		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		s.attr_done = true;
+	}
+	if (s.nt != g.nt || s.smem != g.smem) {
+		int n = 0;
+		CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, g.nt, g.smem));
+		s.nt = g.nt;
+		s.smem = g.smem;
+		s.resident = n < 1 ? 1 : n;
+	}
+	*resident = s.resident;
+	return FIR_GPU_OK;
+}
+
 template <int BITS, bool BE>
 int launch_decode(fir_gpu_ctx* c, cudaStream_t st, const unsigned char* pcm, int64_t avail_lo, int64_t avail_hi,
                   int64_t g0, int64_t n_x, int ch, double* x, int64_t x_pitch)
 {
 	const int fb = ch * (BITS / 8);
 	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
-	bool& attr_done = c->codec_attr[(BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
-	if (!attr_done) {
-		CU_TRY(cudaFuncSetAttribute(pcm_decode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                            CODEC_SMEM_MAX));
-		attr_done = true;
-	}
+	int resident = 0;
+	int rc = codec_residency(c, (BITS / 8 - 2) * 2 + (BE ? 1 : 0), (const void*) pcm_decode_kernel<BITS, BE>, g, &resident);
+	if (rc) return rc;
 	const int64_t tiles = (n_x + g.frames - 1) / g.frames;
-	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * g.ctas_per_sm);
+	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * resident);
 	pcm_decode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(pcm, avail_lo, avail_hi, g0, n_x, ch, x, x_pitch,
 	                                                          g.frames);
 	CU_TRY(cudaGetLastError());
@@ -363,14 +389,11 @@ int launch_encode(fir_gpu_ctx* c, cudaStream_t st, const double* y, int64_t y_pi
 {
 	const int fb = ch * (BITS / 8);
 	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
-	bool& attr_done = c->codec_attr[6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0)];
-	if (!attr_done) {
-		CU_TRY(cudaFuncSetAttribute(pcm_encode_kernel<BITS, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                            CODEC_SMEM_MAX));
-		attr_done = true;
-	}
+	int resident = 0;
+	int rc = codec_residency(c, 6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0), (const void*) pcm_encode_kernel<BITS, BE>, g, &resident);
+	if (rc) return rc;
 	const int64_t tiles = (frames + g.frames - 1) / g.frames;
-	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * g.ctas_per_sm);
+	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * resident);
 	pcm_encode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(y, y_pitch, frames, ch, gain, pcm, g.frames);
 	CU_TRY(cudaGetLastError());
 	c->other_launches++;
@@ -1138,6 +1161,125 @@ int fir_gpu_peak_recompute(fir_gpu_ctx* c, double* peak)
 	return FIR_GPU_OK;
 }
 
+// -------------------------------------------- peak over sample blocks (NCCL)
+
+namespace {
+
+// The few NCCL entry points needed, resolved from libnccl.so.2 at first use: the library is large
+// and a single-GPU run (the common case of the CLI) never pays for loading it.
+typedef struct ncclComm* nccl_comm_t;
+struct NcclApi {
+	void* handle = nullptr;
+	int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+	int (*CommDestroy)(nccl_comm_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+	std::string error;
+};
+constexpr int NCCL_UINT64 = 5, NCCL_MAX = 2; // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since 2.0)
+
+NcclApi& nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+			api.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+			if (api.handle) break;
+		}
+		if (!api.handle) {
+			api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+			return;
+		}
+		auto sym = [&](const char* n) {
+			void* p = dlsym(api.handle, n);
+			if (!p && api.error.empty()) api.error = std::string("libnccl lacks ") + n;
+			return p;
+		};
+		api.CommInitAll = (decltype(api.CommInitAll)) sym("ncclCommInitAll");
+		api.CommDestroy = (decltype(api.CommDestroy)) sym("ncclCommDestroy");
+		api.GroupStart = (decltype(api.GroupStart)) sym("ncclGroupStart");
+		api.GroupEnd = (decltype(api.GroupEnd)) sym("ncclGroupEnd");
+		api.AllReduce = (decltype(api.AllReduce)) sym("ncclAllReduce");
+		api.GetErrorString = (decltype(api.GetErrorString)) sym("ncclGetErrorString");
+	});
+	return api;
+}
+
+struct CommSet {
+	std::vector<int> devices;
+	std::vector<nccl_comm_t> comms;
+};
+std::mutex g_comm_mutex;
+std::deque<CommSet> g_comm_sets;  // kept for the life of the process; a deque: references stay valid as it grows
+
+int comm_set_for(fir_gpu_ctx* const* ctxs, int n, CommSet** out)
+{
+	if (!ctxs || n < 1) return fail(FIR_GPU_ERR_INVALID, "no contexts");
+	std::vector<int> devs;
+	for (int i = 0; i < n; ++i) {
+		if (!ctxs[i]) return fail(FIR_GPU_ERR_INVALID, "null context");
+		devs.push_back(ctxs[i]->device);
+	}
+	for (int i = 0; i < n; ++i)
+		for (int j = i + 1; j < n; ++j)
+			if (devs[i] == devs[j]) return fail(FIR_GPU_ERR_INVALID, "sample blocks must live on distinct devices");
+	NcclApi& api = nccl_api();
+	if (!api.error.empty()) return fail(FIR_GPU_ERR_STATE, "NCCL unavailable: " + api.error);
+	std::lock_guard<std::mutex> lock(g_comm_mutex);
+	for (CommSet& s : g_comm_sets)
+		if (s.devices == devs) {
+			*out = &s;
+			return FIR_GPU_OK;
+		}
+	CommSet s;
+	s.devices = devs;
+	s.comms.resize(n);
+	const int rc = api.CommInitAll(s.comms.data(), n, devs.data());
+	if (rc != 0) return fail(FIR_GPU_ERR_CUDA, std::string("ncclCommInitAll: ") + api.GetErrorString(rc));
+	g_comm_sets.push_back(std::move(s));
+	*out = &g_comm_sets.back();
+	return FIR_GPU_OK;
+}
+
+} // namespace
+
+int fir_gpu_comm_prepare(fir_gpu_ctx* const* ctxs, int n)
+{
+	if (n == 1) return ctxs && ctxs[0] ? FIR_GPU_OK : fail(FIR_GPU_ERR_INVALID, "null context");
+	CommSet* s = nullptr;
+	return comm_set_for(ctxs, n, &s);
+}
+
+int fir_gpu_allreduce_peak(fir_gpu_ctx* const* ctxs, int n, double* peak)
+{
+	if (!ctxs || n < 1 || !peak) return fail(FIR_GPU_ERR_INVALID, "null argument");
+	for (int i = 0; i < n; ++i)
+		if (!ctxs[i] || !ctxs[i]->parked) return fail(FIR_GPU_ERR_STATE, "no filtered signal is parked on a context");
+	if (n > 1) {
+		CommSet* s = nullptr;
+		int rc = comm_set_for(ctxs, n, &s);
+		if (rc) return rc;
+		NcclApi& api = nccl_api();
+		std::lock_guard<std::mutex> lock(g_comm_mutex); // one collective of a device set at a time
+		// non-negative doubles order like their bit patterns: the scalar the FIR epilogue maintains
+		// with atomicMax is reduced as the unsigned integer it is
+		rc = api.GroupStart();
+		for (int i = 0; i < n && rc == 0; ++i)
+			rc = api.AllReduce(ctxs[i]->d_peak, ctxs[i]->d_peak, 1, NCCL_UINT64, NCCL_MAX, s->comms[i], ctxs[i]->stream);
+		const int rc_end = api.GroupEnd();
+		if (rc == 0) rc = rc_end;
+		if (rc != 0) return fail(FIR_GPU_ERR_CUDA, std::string("ncclAllReduce(max): ") + api.GetErrorString(rc));
+		for (int i = 1; i < n; ++i) {
+			DeviceGuard g(ctxs[i]->device);
+			CU_TRY(cudaStreamSynchronize(ctxs[i]->stream));
+		}
+	}
+	return fir_gpu_peak(ctxs[0], peak);
+}
+
 // ------------------------------------------------------------------ encode
 
 int fir_gpu_encode_dev(fir_gpu_ctx* c, double scale, void* pcm_dev)
@@ -1263,6 +1405,27 @@ int fir_gpu_copy_probe(fir_gpu_ctx* c, void* host_buf, size_t bytes, int dir, do
 	CU_TRY(e);
 	*ms = (double) f;
 	return FIR_GPU_OK;
+}
+
+int fir_gpu_reserve(fir_gpu_ctx* c, const fir_gpu_kernel* k, const fir_gpu_pcm* fmt, int host_path)
+{
+	int rc = check_apply_args(c, k, fmt);
+	if (rc) return rc;
+	DeviceGuard g(c->device);
+	const int ch = fmt->channels;
+	const size_t fb = (size_t) ch * (fmt->bits / 8);
+	const int64_t y_pitch = round_up(std::max<int64_t>(fmt->frames, 1), 16);
+	rc = ensure((void**) &c->d_y, &c->y_cap, (size_t) y_pitch * ch * sizeof(double));
+	if (rc) return rc;
+	int64_t max_pitch = 0;
+	for (int mode = 0; mode < (host_path ? 4 : 1); ++mode)
+		for (const auto& [f0, nf] : plan_chunks(c, variant_of(c), fmt->frames, ch, k->n_taps, mode))
+			max_pitch = std::max(max_pitch, x_pitch_for(variant_of(c), nf, k->n_taps));
+	rc = ensure((void**) &c->d_x, &c->x_cap, (size_t) max_pitch * ch * sizeof(double));
+	if (rc || !host_path) return rc;
+	rc = ensure((void**) &c->d_pcm, &c->pcm_cap, (size_t) (fmt->halo_left + fmt->frames + fmt->halo_right) * fb + 32);
+	if (!rc) rc = ensure((void**) &c->d_out, &c->out_cap, (size_t) fmt->frames * fb + 32);
+	return rc;
 }
 
 int fir_gpu_set_codec_geometry(fir_gpu_ctx* c, int tile_bytes, int threads)

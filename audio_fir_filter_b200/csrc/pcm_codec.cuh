@@ -20,7 +20,8 @@ constexpr int CODEC_TILE_BYTES = 16384; // default interleaved bytes staged per 
 constexpr int CODEC_SMEM_MAX = 72 * 1024;
 constexpr int CODEC_UNROLL = 4;         // independent 128-bit global loads a thread keeps in flight
 
-// Geometry of one launch.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x, ...
+// Geometry of one launch.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x, ...; the
+// grid is the number of CTAs resident at once (asked of the runtime at launch).
 // Frames per tile are a multiple of 2*nt when the frame is narrow enough, so that in the planar
 // pass a "row" (nt threads x 2 consecutive frames) never straddles two channels and rows can be
 // unrolled with their loads issued back to back; otherwise a multiple of 32 (generic loop).
@@ -28,7 +29,6 @@ struct CodecGeom {
 	int frames;      // frames per tile
 	int nt;          // threads per CTA
 	unsigned smem;   // dynamic shared memory per CTA
-	int ctas_per_sm; // resident CTAs per SM this geometry allows (grid = SMs x this, at most)
 };
 
 __host__ __device__ inline uint32_t pad_byte(uint32_t b);
@@ -46,10 +46,6 @@ __host__ inline CodecGeom codec_geom(int fb, int tile_bytes = CODEC_TILE_BYTES, 
 	}
 	g.frames = f;
 	g.smem = pad_byte((uint32_t) (f * fb) + 64u) + 16u;
-	int by_smem = (int) ((227u * 1024u) / (g.smem + 1024u)), by_threads = 2048 / nt;
-	g.ctas_per_sm = by_smem < by_threads ? by_smem : by_threads;
-	if (g.ctas_per_sm > 32) g.ctas_per_sm = 32;
-	if (g.ctas_per_sm < 1) g.ctas_per_sm = 1;
 	return g;
 }
 
@@ -126,6 +122,31 @@ __device__ __forceinline__ void store_pcm_bytes(unsigned char* tile, uint32_t b,
 	}
 }
 
+// The same when the caller knows (once per tile, uniformly for the CTA) that every sample offset
+// is a multiple of the sample size: one store, no alignment tests.  Three-byte samples are never
+// "aligned"; they keep the two-store form above.
+template <int NB, bool ALIGNED>
+__device__ __forceinline__ void store_pcm_at(unsigned char* tile, uint32_t b, uint32_t u)
+{
+	if (ALIGNED && NB == 2) *reinterpret_cast<uint16_t*>(tile + pad_byte(b)) = (uint16_t) u;
+	else if (ALIGNED && NB == 4) *reinterpret_cast<uint32_t*>(tile + pad_byte(b)) = u;
+	else store_pcm_bytes<NB>(tile, b, u);
+}
+
+// The sample at logical byte offset b of the skewed tile, in bits 0..8*NB-1 (upper bits unspecified).
+template <int NB, bool ALIGNED>
+__device__ __forceinline__ uint32_t load_pcm_at(const unsigned char* tile, uint32_t b)
+{
+	if (ALIGNED && NB == 2) return *reinterpret_cast<const uint16_t*>(tile + pad_byte(b));
+	if (ALIGNED && NB == 4) return *reinterpret_cast<const uint32_t*>(tile + pad_byte(b));
+	return lds_unaligned_u32(reinterpret_cast<const uint32_t*>(tile), b);
+}
+
+template <bool B>
+struct BoolTag {
+	static constexpr bool value = B;
+};
+
 // Decode a window of the interleaved PCM into the zero-padded planar layout.
 //   pcm            : first byte of logical frame avail_lo
 //   [avail_lo, avail_hi) : logical frames present in pcm (real data)
@@ -197,16 +218,26 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 		int nloc = F;
 		if (i0 + nloc > n_x) nloc = (int) (n_x - i0);
 		if (rows_ok && nloc == F && la == 0 && lb == F) {
-			// whole tile, all of it real data: rows of nt thread-pairs, no per-sample predicates
-			const int rows_per_ch = F / (2 * nt), rows = channels * rows_per_ch;
+			// whole tile, all of it real data: rows of nt thread-pairs (one channel per row, so the
+			// channel and the alignment class are uniform), no per-sample predicates, no division
+			const int rows_per_ch = F / (2 * nt);
+			auto planar = [&](auto tag) {
+				constexpr bool AL = decltype(tag)::value;
+				for (int c = 0; c < channels; ++c) {
+					double* xc = x + (long long) c * x_pitch + i0;
+					const uint32_t ob = mis + (uint32_t) c * NB;
 #pragma unroll 2
-			for (int r = 0; r < rows; ++r) {
-				const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
-				const uint32_t o = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
-				const double v0 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, o)) * inv;
-				const double v1 = (double) pcm_to_int<BITS, BE>(lds_unaligned_u32(tw, o + fb)) * inv;
-				*reinterpret_cast<double2*>(x + (long long) c * x_pitch + i0 + fl) = make_double2(v0, v1);
-			}
+					for (int j = 0; j < rows_per_ch; ++j) {
+						const int fl = 2 * (j * nt + tid);
+						const uint32_t o = ob + (uint32_t) fl * fb;
+						const double v0 = (double) pcm_to_int<BITS, BE>(load_pcm_at<NB, AL>(tile, o)) * inv;
+						const double v1 = (double) pcm_to_int<BITS, BE>(load_pcm_at<NB, AL>(tile, o + fb)) * inv;
+						*reinterpret_cast<double2*>(xc + fl) = make_double2(v0, v1);
+					}
+				}
+			};
+			if (NB != 3 && (mis % NB) == 0) planar(BoolTag<true>{});
+			else planar(BoolTag<false>{});
 		} else {
 			// edge tiles (zero padding, ragged end) and very wide frames: channel by channel, a thread
 			// converts two consecutive frames and stores them with one 128-bit write (i0 and x_pitch
@@ -235,11 +266,22 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 // Persistent CTAs like the decoder.  Per tile: the PLANAR pass (CODEC_UNROLL independent
 // LDG.128 of the parked signal in flight per thread, then quantise and drop the bytes into
 // the skewed tile), then the DRAIN (128-bit coalesced stores of the interleaved bytes).
+// q = clamp(rint(y * gain)): the product is rounded to binary64, converted with round-to-nearest-
+// even and saturation to int32 (one F2I), then clamped as an integer.  rint() is monotone and the
+// limits are integers, so clamping after rounding equals clamping before it -- the FP64
+// min/max pair of the textbook form costs ~16 instructions per sample on this machine, and these
+// kernels are issue-bound, not HBM-bound, until that is gone.
 template <int BITS, bool BE>
-__device__ __forceinline__ uint32_t quantise(double v, double gain, double lo_lim, double hi_lim)
+__device__ __forceinline__ uint32_t quantise(double v, double gain)
 {
-	v = fmin(fmax(v * gain, lo_lim), hi_lim);
-	return int_to_pcm<BITS, BE>((int32_t) __double2ll_rn(v));
+	int q;
+	const double p = __dmul_rn(v, gain);
+	asm("cvt.rni.sat.s32.f64 %0, %1;" : "=r"(q) : "d"(p));
+	if (BITS < 32) {
+		constexpr int LIM = (int) (1ll << (BITS < 32 ? BITS - 1 : 1));
+		q = max(min(q, LIM - 1), -LIM);
+	}
+	return int_to_pcm<BITS, BE>(q);
 }
 
 template <int BITS, bool BE>
@@ -253,7 +295,6 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 	const int nt = blockDim.x, tid = threadIdx.x;
 	const int fb = channels * NB;
 	const long long n_tiles = (frames + F - 1) / F;
-	const double hi_lim = (double) ((1ll << (BITS - 1)) - 1), lo_lim = -(double) (1ll << (BITS - 1));
 	const bool rows_ok = (F % (2 * nt)) == 0;
 
 	for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
@@ -265,28 +306,38 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 		const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p0) & 15u);
 
 		if (rows_ok && nf == F) {
+			// rows of nt thread-pairs, one channel per row: (c, j) advance as CTA-uniform counters,
+			// U rows at a time with all their loads issued before the first is used
 			const int rows_per_ch = F / (2 * nt), rows = channels * rows_per_ch;
-			for (int r0 = 0; r0 < rows; r0 += U) {
-				double2 v[U];
+			auto planar = [&](auto tag) {
+				constexpr bool AL = decltype(tag)::value;
+				int c = 0, j = 0;
+				for (int r0 = 0; r0 < rows; r0 += U) {
+					double2 v[U];
+					uint32_t o[U];
 #pragma unroll
-				for (int k = 0; k < U; ++k) { // all the loads first
-					const int r = r0 + k;
-					if (r < rows) {
-						const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
-						v[k] = __ldg(reinterpret_cast<const double2*>(y + (long long) c * y_pitch + f0 + fl));
+					for (int k = 0; k < U; ++k) {
+						if (r0 + k < rows) {
+							const int fl = 2 * (j * nt + tid);
+							o[k] = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
+							v[k] = __ldg(reinterpret_cast<const double2*>(y + (long long) c * y_pitch + f0 + fl));
+							if (++j == rows_per_ch) {
+								j = 0;
+								++c;
+							}
+						}
+					}
+#pragma unroll
+					for (int k = 0; k < U; ++k) {
+						if (r0 + k < rows) {
+							store_pcm_at<NB, AL>(tile, o[k], quantise<BITS, BE>(v[k].x, gain));
+							store_pcm_at<NB, AL>(tile, o[k] + fb, quantise<BITS, BE>(v[k].y, gain));
+						}
 					}
 				}
-#pragma unroll
-				for (int k = 0; k < U; ++k) {
-					const int r = r0 + k;
-					if (r < rows) {
-						const int c = r / rows_per_ch, fl = 2 * ((r - c * rows_per_ch) * nt + tid);
-						const uint32_t o = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
-						store_pcm_bytes<NB>(tile, o, quantise<BITS, BE>(v[k].x, gain, lo_lim, hi_lim));
-						store_pcm_bytes<NB>(tile, o + fb, quantise<BITS, BE>(v[k].y, gain, lo_lim, hi_lim));
-					}
-				}
-			}
+			};
+			if (NB != 3 && (mis % NB) == 0) planar(BoolTag<true>{});
+			else planar(BoolTag<false>{});
 		} else {
 			// ragged last tile and very wide frames: channel by channel, two consecutive frames per
 			// thread (one 128-bit load when both exist)
@@ -303,10 +354,8 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 					} else {
 						v0 = yc[fl];
 					}
-					store_pcm_bytes<NB>(tile, dc + (uint32_t) fl * fb, quantise<BITS, BE>(v0, gain, lo_lim, hi_lim));
-					if (two)
-						store_pcm_bytes<NB>(tile, dc + (uint32_t) (fl + 1) * fb,
-						                    quantise<BITS, BE>(v1, gain, lo_lim, hi_lim));
+					store_pcm_bytes<NB>(tile, dc + (uint32_t) fl * fb, quantise<BITS, BE>(v0, gain));
+					if (two) store_pcm_bytes<NB>(tile, dc + (uint32_t) (fl + 1) * fb, quantise<BITS, BE>(v1, gain));
 				}
 			}
 		}

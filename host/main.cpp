@@ -29,8 +29,6 @@ using namespace lowcut;
 
 int main(int argc, char** argv)
 {
-	const auto t_main = std::chrono::steady_clock::now();
-	auto since_start = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_main).count(); };
 	int exit_val = EXIT_SUCCESS;
 	try {
 		const CliOptions cli = parse_cli(argc, argv);
@@ -66,9 +64,9 @@ int main(int argc, char** argv)
 			// the reference removes an existing output up front (main.cp:107); here the result is
 			// written to <out>.part and renamed over the old file only once it is complete, so a
 			// failure leaves the old output in place
-			if (opts.verbose) std::cout << std::format("  [{:8.3f} s] devices counted", since_start()) << std::endl;
+			if (opts.verbose) std::cout << std::format("  [{:8.3f} s since start] devices counted", uptime()) << std::endl;
 			process_file(in, out, opts, pool);
-			if (opts.verbose) std::cout << std::format("  [{:8.3f} s] done", since_start()) << std::endl;
+			if (opts.verbose) std::cout << std::format("  [{:8.3f} s since start] done", uptime()) << std::endl;
 			leave_now();
 		} else {
 			// Scenario 2: input files -> output directory (main.cp:112-148)

@@ -22,6 +22,7 @@ namespace lowcut {
 namespace {
 
 std::mutex g_io; // serialises stdout between the per-GPU workers
+const auto g_loaded = std::chrono::steady_clock::now();
 
 void say(const std::string& s)
 {
@@ -227,6 +228,11 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		std::vector<std::exception_ptr> errs(world);
 		std::atomic<bool> failed{false};
 		std::barrier sync((std::ptrdiff_t) world + 1);
+		// Sample-block mode: the peak is one ncclAllReduce(max) over the blocks' device scalars.
+		// The communicator comes up on its own thread while the blocks are read and filtered.
+		std::vector<fir_gpu_ctx*> block_ctxs(ctxs.begin(), ctxs.begin() + (std::ptrdiff_t) world);
+		std::thread comm_up;
+		if (world > 1) comm_up = std::thread([&] { fir_gpu_comm_prepare(block_ctxs.data(), (int) world); });
 		std::vector<std::thread> th;
 		for (size_t r = 0; r < world; ++r)
 			th.emplace_back([&, r] {
@@ -248,10 +254,24 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				}
 			});
 		sync.arrive_and_wait();
+		if (comm_up.joinable()) comm_up.join();
 		stamp("filtered, peak known");
 		try {
 			if (!failed) {
-				peak = *std::max_element(peaks.begin(), peaks.end());     // host max over the GPUs' peaks
+				// ProcessFile.cp:92-96 is a max over the whole file: all-reduce MAX of the blocks' peaks
+				// (NCCL over NVLink, on the device scalars).  Without a loadable NCCL the n doubles that
+				// fir_gpu_peak already brought back are compared here instead.
+				const char* how = "single block";
+				if (world > 1 && !std::getenv("LOWCUT_NO_NCCL") &&
+				    fir_gpu_allreduce_peak(block_ctxs.data(), (int) world, &peak) == FIR_GPU_OK) {
+					how = "ncclAllReduce(max) over the blocks";
+					if (peak != *std::max_element(peaks.begin(), peaks.end()))
+						throw GpuError(FIR_GPU_ERR_STATE, "the all-reduced peak is not the max of the block peaks");
+				} else {
+					if (world > 1) how = "host max of the blocks' peaks (NCCL not used)";
+					peak = *std::max_element(peaks.begin(), peaks.end());
+				}
+				status(std::format("  peak exchange: {}", how));
 				scale = scale_for_peak(peak, opts.normalize);             // ProcessFile.cp:98-101
 				if (scale != 1.0) status("Doing audio normalize.");
 				status("Writing output file.");
@@ -285,6 +305,8 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 }
 
 } // namespace
+
+double uptime() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_loaded).count(); }
 
 double scale_for_peak(double peak, bool normalize)
 {
@@ -394,6 +416,7 @@ void process_file(const std::filesystem::path& input_path, const std::filesystem
 	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
 	std::vector<size_t> slots;
 	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, 1, &slots);
+	if (opts.verbose) say(std::format("  [{:8.3f} s since start] {} GPU context(s) ready", uptime(), ctxs.size()));
 	run_file(input_path, output_path, opts, pool, ctxs, slots);
 }
 

@@ -75,6 +75,9 @@ void process_file(const std::filesystem::path& input_path, const std::filesystem
 void process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
                    const FilterOptions& opts, GpuPool& pool);
 
+// Seconds since the program was loaded (the -v time stamps; start-up cost is part of what a user waits for).
+double uptime();
+
 // ProcessFile.cp:98: normalise when the peak exceeds full scale or -n is given.
 double scale_for_peak(double peak, bool normalize);
 

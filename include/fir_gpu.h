@@ -174,6 +174,24 @@ FIR_GPU_API int fir_gpu_peak_dev(fir_gpu_ctx *ctx, void **peak_dev);
  * kernel instead of the value fused into the FIR epilogue. */
 FIR_GPU_API int fir_gpu_peak_recompute(fir_gpu_ctx *ctx, double *peak);
 
+/* ---- the peak over sample blocks on several GPUs  (ProcessFile.cp:92-96) -- */
+
+/* Sample-block mode: one long file, one contiguous block per device, every block
+ * filtered on its own context of THIS process.  The reference's peak is a max over the
+ * whole file, so the per-device peaks are max-reduced with ONE ncclAllReduce(ncclMax) of
+ * the 8-byte device scalars over NVLink, in place and ordered on each context's stream;
+ * afterwards every context holds the global peak (fir_gpu_peak / fir_gpu_peak_dev return
+ * it) and *peak receives it.  This is the only collective of the whole path.
+ * The communicator of a device set is created on first use and kept;
+ * fir_gpu_comm_prepare creates it ahead of time (from another host thread, while the
+ * blocks are still being filtered).  NCCL (libnccl.so.2) is loaded on first use:
+ * FIR_GPU_ERR_STATE when it cannot be -- the caller may then take the max of the
+ * fir_gpu_peak values itself (n doubles; nothing is computed on the CPU either way).
+ * One-process-per-GPU hosts (torch.distributed, MPI) run their own all-reduce on
+ * fir_gpu_peak_dev instead. */
+FIR_GPU_API int fir_gpu_comm_prepare(fir_gpu_ctx *const *ctxs, int n);
+FIR_GPU_API int fir_gpu_allreduce_peak(fir_gpu_ctx *const *ctxs, int n, double *peak);
+
 /* ---- fir_gpu_encode  (ProcessFile.cp:100,117) ---------------------------- */
 
 /* Encode phase: q = clamp(rint(y * scale * 2^(bits-1))) (ties to even, clamp to

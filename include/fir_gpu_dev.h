@@ -34,6 +34,11 @@ FIR_GPU_API int fir_gpu_fp64_peak(fir_gpu_ctx *ctx, int kind, double seconds, do
  * are compared with (N ranks call it at the same moment). */
 FIR_GPU_API int fir_gpu_copy_probe(fir_gpu_ctx *ctx, void *host_buf, size_t bytes, int dir, double *ms);
 
+/* Allocate now every device buffer an apply of this format with this kernel will need
+ * (host_path != 0: the staging buffers of the host-buffer entry points too), so that a
+ * single timed pass does not measure cudaMalloc of tens of gigabytes. */
+FIR_GPU_API int fir_gpu_reserve(fir_gpu_ctx *ctx, const fir_gpu_kernel *k, const fir_gpu_pcm *fmt, int host_path);
+
 /* FIR kernel variant (0 = default).  The product build carries the default DMMA
  * kernel and one DFMA comparison kernel; -DFIR_ALL_VARIANTS adds the shapes of the
  * tuning sweeps (tools/sweep_variants.py). */

@@ -20,6 +20,18 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    # both thread rows of SURVEY.md 8d, the whole file timed once (config 1 fits), and a label
+    # saying what the CPU figure times
+    rows = d["cpu_baseline"]["rows"]
+    assert len(rows) == 2 and rows[0]["threads"] >= rows[1]["threads"] >= 1
+    assert "main.cp:75" in rows[1]["row"]
+    assert d["cpu_baseline"]["whole_file"]["value"] > 0
+    assert "decode + FIR + peak" in d["cpu_baseline"]["times"]
+    # the config object is the one the GPU arm prints for the same arguments, key for key
+    sys.path.insert(0, ROOT)
+    from bench import CONFIGS, METRIC, config_dict
+
+    assert d["config"] == config_dict(CONFIGS[1], 1, "block") and d["metric"] == METRIC
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
@@ -62,6 +74,15 @@ def test_gpu_arm_prints_the_full_contract_line():
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "f64"
     assert d["gpu_launches"] == 3 * 3                     # decode + FIR + encode per step, all ours
+    sys.path.insert(0, ROOT)
+    from bench import CONFIGS, config_dict
+
+    assert d["config"] == config_dict(CONFIGS[1], 1, "block")     # same object as the reference arm's
+    p = d["parity"]
+    assert p["ok"] is True and p["windows"] >= 4 and p["worst_d3"] <= 1e-12 and p["max_flip_lsb"] <= 1
+    assert p["pcm_windows"] >= 2 * p["windows"] and p["global_peak_is_max_of_block_peaks"] is True
+    assert d["e2e"]["pipelined"]["matches_serial_arm"] is True and d["e2e"]["copy_ceiling"]["d2h_gbs_per_rank"] > 1
+    assert d["roofline"]["traffic_source"]
     e = d["e2e"]
     assert 0 < e["value"] < d["value"] and e["matches_device_arm"] is True
     assert e["h2d_bytes_per_step"] == 2_880_000 * 6 and e["d2h_bytes_per_step"] == 2_880_000 * 6 + 8

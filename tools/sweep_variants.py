@@ -7,7 +7,12 @@ import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the product library carries two FIR shapes; the sweep needs the -DFIR_ALL_VARIANTS build
+SWEEP_LIB = os.path.join(ROOT, "audio_fir_filter_b200", "libfir_gpu_sweep.so")
+if "FIR_GPU_LIB" not in os.environ and os.path.exists(SWEEP_LIB):
+    os.environ["FIR_GPU_LIB"] = SWEEP_LIB
 import torch  # noqa: E402
 
 from audio_fir_filter_b200 import capi  # noqa: E402
