@@ -110,7 +110,7 @@ DEV_SYMBOLS = {
     "fir_gpu_set_variant": (C.c_int, [_vp, C.c_int]),
     "fir_gpu_variant_count": (C.c_int, []),
     "fir_gpu_variant_name": (C.c_char_p, [C.c_int]),
-    "fir_gpu_set_codec_geometry": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "fir_gpu_set_codec_geometry": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "fir_gpu_test_fail_next_create": (C.c_int, [C.c_int]),
     "fir_gpu_set_x_budget": (C.c_int, [_vp, _i64]),
 }
@@ -366,8 +366,8 @@ class Context:
         fmt = self._fmt(frames, channels, bits, big_endian, halo_left, halo_right)
         _check(lib().fir_gpu_reserve(self._h, kernel._h, C.byref(fmt), int(host_path)))
 
-    def set_codec_geometry(self, tile_bytes: int, threads: int) -> None:
-        _check(lib().fir_gpu_set_codec_geometry(self._h, tile_bytes, threads))
+    def set_codec_geometry(self, tile_bytes: int, threads: int, carveout_pct: int = 50) -> None:
+        _check(lib().fir_gpu_set_codec_geometry(self._h, tile_bytes, threads, carveout_pct))
 
     def set_variant(self, variant: int) -> None:
         _check(lib().fir_gpu_set_variant(self._h, variant))

@@ -213,9 +213,10 @@ struct fir_gpu_ctx {
 	// cudaFuncSetAttribute is per device: remember what this context's device has
 	struct CodecSlot {
 		bool attr_done = false;
-		int nt = 0, resident = 0;
+		int nt = 0, resident = 0, carveout = -2;
 		unsigned smem = 0;
 	} codec_slot[12];
+	int codec_carveout = CODEC_CARVEOUT; // percent of the SM's array given to shared memory (-1: driver's choice)
 	int codec_tile_bytes = CODEC_TILE_BYTES, codec_nt = CODEC_NT;
 	std::vector<char> fir_attr;
 };
@@ -343,6 +344,14 @@ int check_fmt(const fir_gpu_pcm* f)
 	return FIR_GPU_OK;
 }
 
+// The tile counter of a codec launch (pcm_codec.cuh: next_tile).  Launches that may overlap on
+// the device never share one: decode and encode have their own, and so has each stream.
+unsigned long long* tile_counter_for(fir_gpu_ctx* c, int encode, cudaStream_t st)
+{
+	const int stream_slot = st == c->d2h_stream ? 1 : 0;
+	return c->d_peak + 2 + 2 * encode + stream_slot; // slots 2..5 of the 64-byte scratch (0: peak, 1: peak recompute)
+}
+
 // CTAs of a codec kernel that are resident per SM at this geometry -- asked of the runtime, not
 // estimated: the persistent grid must be exactly one wave (a CTA that does not fit starts when
 // another finishes, i.e. at the very end, and runs its share of the tiles almost alone).
@@ -351,8 +360,12 @@ int codec_residency(fir_gpu_ctx* c, int slot, const void* fn, const CodecGeom& g
 	fir_gpu_ctx::CodecSlot& s = c->codec_slot[slot];
 	if (!s.attr_done) {
 		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, CODEC_SMEM_MAX));
-		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		s.attr_done = true;
+	}
+	if (s.carveout != c->codec_carveout) {
+		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, c->codec_carveout));
+		s.carveout = c->codec_carveout;
+		s.nt = 0; // residency depends on it
 	}
 	if (s.nt != g.nt || s.smem != g.smem) {
 		int n = 0;
@@ -370,14 +383,14 @@ int launch_decode(fir_gpu_ctx* c, cudaStream_t st, const unsigned char* pcm, int
                   int64_t g0, int64_t n_x, int ch, double* x, int64_t x_pitch)
 {
 	const int fb = ch * (BITS / 8);
-	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
+	const CodecGeom g = codec_geom(fb, ch, c->codec_tile_bytes, c->codec_nt);
 	int resident = 0;
 	int rc = codec_residency(c, (BITS / 8 - 2) * 2 + (BE ? 1 : 0), (const void*) pcm_decode_kernel<BITS, BE>, g, &resident);
 	if (rc) return rc;
 	const int64_t tiles = (n_x + g.frames - 1) / g.frames;
 	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * resident);
 	pcm_decode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(pcm, avail_lo, avail_hi, g0, n_x, ch, x, x_pitch,
-	                                                          g.frames);
+	                                                          g.frames, tile_counter_for(c, 0, st));
 	CU_TRY(cudaGetLastError());
 	c->other_launches++;
 	return FIR_GPU_OK;
@@ -388,13 +401,14 @@ int launch_encode(fir_gpu_ctx* c, cudaStream_t st, const double* y, int64_t y_pi
                   double gain, unsigned char* pcm)
 {
 	const int fb = ch * (BITS / 8);
-	const CodecGeom g = codec_geom(fb, c->codec_tile_bytes, c->codec_nt);
+	const CodecGeom g = codec_geom(fb, ch, c->codec_tile_bytes, c->codec_nt);
 	int resident = 0;
 	int rc = codec_residency(c, 6 + (BITS / 8 - 2) * 2 + (BE ? 1 : 0), (const void*) pcm_encode_kernel<BITS, BE>, g, &resident);
 	if (rc) return rc;
 	const int64_t tiles = (frames + g.frames - 1) / g.frames;
 	const unsigned blocks = (unsigned) std::min<int64_t>(tiles, (int64_t) c->sm_count * resident);
-	pcm_encode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(y, y_pitch, frames, ch, gain, pcm, g.frames);
+	pcm_encode_kernel<BITS, BE><<<blocks, g.nt, g.smem, st>>>(y, y_pitch, frames, ch, gain, pcm, g.frames,
+	                                                          tile_counter_for(c, 1, st));
 	CU_TRY(cudaGetLastError());
 	c->other_launches++;
 	return FIR_GPU_OK;
@@ -1428,14 +1442,17 @@ int fir_gpu_reserve(fir_gpu_ctx* c, const fir_gpu_kernel* k, const fir_gpu_pcm* 
 	return rc;
 }
 
-int fir_gpu_set_codec_geometry(fir_gpu_ctx* c, int tile_bytes, int threads)
+int fir_gpu_set_codec_geometry(fir_gpu_ctx* c, int tile_bytes, int threads, int smem_carveout_pct)
 {
 	if (!c) return fail(FIR_GPU_ERR_INVALID, "null context");
 	if (threads != 128 && threads != 256) return fail(FIR_GPU_ERR_INVALID, "codec threads must be 128 or 256");
-	if (tile_bytes < 4096 || tile_bytes > 65536 - 4096)
-		return fail(FIR_GPU_ERR_INVALID, "codec tile must be 4 KiB .. 60 KiB");
+	if (tile_bytes != 0 && (tile_bytes < 4096 || tile_bytes > 65536 - 4096))
+		return fail(FIR_GPU_ERR_INVALID, "codec tile must be 0 (default: 4096 samples) or 4 KiB .. 60 KiB");
+	if (smem_carveout_pct < -1 || smem_carveout_pct > 100)
+		return fail(FIR_GPU_ERR_INVALID, "carveout must be -1 (driver's choice) or 0..100 percent");
 	c->codec_tile_bytes = tile_bytes;
 	c->codec_nt = threads;
+	c->codec_carveout = smem_carveout_pct;
 	return FIR_GPU_OK;
 }
 

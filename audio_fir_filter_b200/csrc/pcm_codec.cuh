@@ -16,8 +16,10 @@
 namespace firgpu {
 
 constexpr int CODEC_NT = 256;           // default threads per CTA (128 and 256 are supported)
-constexpr int CODEC_TILE_BYTES = 16384; // default interleaved bytes staged per tile
+constexpr int CODEC_TILE_BYTES = 0;     // interleaved bytes staged per tile; 0 = CODEC_TILE_SAMPLES samples
+constexpr int CODEC_TILE_SAMPLES = 4096; // default tile: 32 KB on the planar FP64 side whatever the PCM format
 constexpr int CODEC_SMEM_MAX = 72 * 1024;
+constexpr int CODEC_CARVEOUT = 50;      // default shared-memory carveout of the codec kernels, percent
 constexpr int CODEC_UNROLL = 4;         // independent 128-bit global loads a thread keeps in flight
 
 // Geometry of one launch.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x, ...; the
@@ -33,10 +35,13 @@ struct CodecGeom {
 
 __host__ __device__ inline uint32_t pad_byte(uint32_t b);
 
-__host__ inline CodecGeom codec_geom(int fb, int tile_bytes = CODEC_TILE_BYTES, int nt = CODEC_NT)
+// The default tile holds CODEC_TILE_SAMPLES samples: the planar side (8 B a sample) is what the
+// HBM time goes to, and a launch over a 100 MB file must still give every resident CTA a dozen
+// tiles, or the CTAs that draw the last ones finish a tile-time after the others.
+__host__ inline CodecGeom codec_geom(int fb, int channels, int tile_bytes = CODEC_TILE_BYTES, int nt = CODEC_NT)
 {
 	CodecGeom g;
-	int f = tile_bytes / fb;
+	int f = tile_bytes > 0 ? tile_bytes / fb : CODEC_TILE_SAMPLES / channels;
 	if (f < 2 * nt && nt > 128 && f >= 256) nt = 128; // wide frames: rows of 128 thread-pairs still fit
 	g.nt = nt;
 	if (f >= 2 * nt) f = f / (2 * nt) * (2 * nt);
@@ -142,6 +147,38 @@ __device__ __forceinline__ uint32_t load_pcm_at(const unsigned char* tile, uint3
 	return lds_unaligned_u32(reinterpret_cast<const uint32_t*>(tile), b);
 }
 
+// 16 bytes that are read exactly once: bypass L1 allocation (the in-flight loads of a streaming
+// kernel must not depend on how much of the SM's array is left to L1 once the tile is carved out).
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p)
+{
+	double2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u32x4(const void* p)
+{
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+	             : "l"(p));
+	return v;
+}
+
+// Dynamic tile scheduler of the persistent codec CTAs: tiles are handed out by one global counter,
+// so the CTAs finish together whatever n_tiles / gridDim is (a static stride leaves up to one tile
+// per CTA of imbalance -- 10 % of a 100 us launch).  Every CTA fetches until it is told "no more":
+// n_tiles + gridDim fetches in all, and whoever draws the last one puts the counter back to zero
+// for the next launch on the stream.  Thread 0 fetches (into a shared slot) right after a tile's
+// first barrier, so that the atomic's latency hides under the second half of the tile; everybody
+// reads the slot after the tile's last barrier.
+__device__ __forceinline__ long long fetch_tile(unsigned long long* counter, long long n_tiles)
+{
+	const unsigned long long t = atomicAdd(counter, 1ull);
+	if (t == (unsigned long long) n_tiles + gridDim.x - 1) *counter = 0ull; // the last fetch of the launch
+	return (long long) t;
+}
+
 template <bool B>
 struct BoolTag {
 	static constexpr bool value = B;
@@ -160,11 +197,13 @@ struct BoolTag {
 template <int BITS, bool BE>
 __global__ void __launch_bounds__(256)
 pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, long long avail_hi,
-                  long long g0, long long n_x, int channels, double* __restrict__ x, long long x_pitch, int F)
+                  long long g0, long long n_x, int channels, double* __restrict__ x, long long x_pitch, int F,
+                  unsigned long long* __restrict__ tile_counter)
 {
 	constexpr int NB = BITS / 8;
 	constexpr int U = CODEC_UNROLL;
 	extern __shared__ __align__(16) unsigned char tile[];
+	__shared__ long long tile_slot;
 	const int nt = blockDim.x, tid = threadIdx.x;
 	const int fb = channels * NB;
 	const long long n_tiles = (n_x + F - 1) / F;
@@ -172,7 +211,9 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 	const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
 	const bool rows_ok = (F % (2 * nt)) == 0;
 
-	for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+	if (tid == 0) tile_slot = fetch_tile(tile_counter, n_tiles);
+	__syncthreads();
+	for (long long tl = tile_slot; tl < n_tiles; tl = tile_slot) {
 		const long long i0 = tl * F;
 		// logical frames of this tile that exist in pcm
 		long long ga = g0 + i0, gb = ga + F;
@@ -194,7 +235,7 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 				for (int k = 0; k < U; ++k) { // all the loads first: U x 16 B in flight per thread
 					const uint32_t v = v0 + k * nt, lo = v << 4;
 					full[k] = v < nvec && lo >= mis && lo + 16 <= end;
-					if (full[k]) q[k] = __ldg(reinterpret_cast<const uint4*>(base + lo)); // 128-bit coalesced
+					if (full[k]) q[k] = ldg_stream_u32x4(base + lo); // 128-bit coalesced, read once
 				}
 #pragma unroll
 				for (int k = 0; k < U; ++k) {
@@ -213,6 +254,7 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 			}
 		}
 		__syncthreads();
+		if (tid == 0) tile_slot = fetch_tile(tile_counter, n_tiles); // the next tile; read after the barrier below
 
 		const int la = (int) (ga - g0 - i0), lb = (int) (gb - g0 - i0); // tile-local frames present in pcm
 		int nloc = F;
@@ -256,7 +298,7 @@ pcm_decode_kernel(const unsigned char* __restrict__ pcm, long long avail_lo, lon
 				}
 			}
 		}
-		__syncthreads(); // the tile is refilled by the next trip
+		__syncthreads(); // the tile is refilled by the next trip; tile_slot holds the next tile
 	}
 }
 
@@ -287,17 +329,20 @@ __device__ __forceinline__ uint32_t quantise(double v, double gain)
 template <int BITS, bool BE>
 __global__ void __launch_bounds__(256)
 pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long frames, int channels,
-                  double gain, unsigned char* __restrict__ pcm, int F)
+                  double gain, unsigned char* __restrict__ pcm, int F, unsigned long long* __restrict__ tile_counter)
 {
 	constexpr int NB = BITS / 8;
 	constexpr int U = CODEC_UNROLL;
 	extern __shared__ __align__(16) unsigned char tile[];
+	__shared__ long long tile_slot;
 	const int nt = blockDim.x, tid = threadIdx.x;
 	const int fb = channels * NB;
 	const long long n_tiles = (frames + F - 1) / F;
 	const bool rows_ok = (F % (2 * nt)) == 0;
 
-	for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+	if (tid == 0) tile_slot = fetch_tile(tile_counter, n_tiles);
+	__syncthreads();
+	for (long long tl = tile_slot; tl < n_tiles; tl = tile_slot) {
 		const long long f0 = tl * F;
 		long long f1 = f0 + F;
 		if (f1 > frames) f1 = frames;
@@ -320,7 +365,7 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 						if (r0 + k < rows) {
 							const int fl = 2 * (j * nt + tid);
 							o[k] = mis + (uint32_t) c * NB + (uint32_t) fl * fb;
-							v[k] = __ldg(reinterpret_cast<const double2*>(y + (long long) c * y_pitch + f0 + fl));
+							v[k] = ldg_stream_f64x2(y + (long long) c * y_pitch + f0 + fl);
 							if (++j == rows_per_ch) {
 								j = 0;
 								++c;
@@ -360,6 +405,7 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 			}
 		}
 		__syncthreads();
+		if (tid == 0) tile_slot = fetch_tile(tile_counter, n_tiles); // the next tile; read after the barrier below
 
 		unsigned char* base = p0 - mis;
 		const uint32_t end = mis + (uint32_t) nf * fb;
@@ -374,7 +420,7 @@ pcm_encode_kernel(const double* __restrict__ y, long long y_pitch, long long fra
 				for (uint32_t s = a; s < b; ++s) base[s] = tile[pad_byte(s)];
 			}
 		}
-		__syncthreads(); // the tile is rewritten by the next trip
+		__syncthreads(); // the tile is rewritten by the next trip; tile_slot holds the next tile
 	}
 }
 

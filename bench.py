@@ -447,8 +447,8 @@ class Env:
         self.ctx.set_stream(self.stream.cuda_stream)
         if a.variant >= 0:
             self.ctx.set_variant(a.variant)
-        if a.codec_tile or a.codec_threads:
-            self.ctx.set_codec_geometry(a.codec_tile or 16384, a.codec_threads or 256)
+        if a.codec_tile or a.codec_threads or a.codec_carveout != 50:
+            self.ctx.set_codec_geometry(a.codec_tile, a.codec_threads or 256, a.codec_carveout)
         self._ctx2 = None
         # measured FP64 ceilings of this GPU, before the run (register-resident probes)
         self.dfma_peak = self.ctx.fp64_peak(0, 0.25)
@@ -665,6 +665,17 @@ def run_workload(env: Env, cfg_id: int, *, steps: int, warmup: int, mode: str = 
                 cc[f"{name}_ms"] = best
                 cc[f"{name}_gbs_per_rank"] = n / (best * 1e-3) / 1e9
                 cc[f"{name}_gbs_aggregate"] = world * n / (best * 1e-3) / 1e9
+            # the same download into a buffer pinned by somebody else's allocator (torch: cudaHostAlloc
+            # with default flags, not cudaHostAllocPortable): is the rate a property of OUR buffers?
+            tp = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+            best = None
+            for _ in range(3):
+                barrier()
+                ms = ctx.copy_probe(tp.data_ptr(), out_bytes, 1)
+                (ms,) = env.max_over_ranks(ms) if world > 1 else (ms,)
+                best = ms if best is None else min(best, ms)
+            cc["d2h_gbs_per_rank_torch_pinned_buffer"] = out_bytes / (best * 1e-3) / 1e9
+            del tp
             if world > 1:                                                   # one rank alone, the others idle
                 barrier()
                 alone = ctx.copy_probe(h_out.array, out_bytes, 1) if rank == 0 else 0.0
@@ -916,6 +927,7 @@ def main() -> int:
     ap.add_argument("--variant", type=int, default=-1, help="FIR kernel variant (experiments)")
     ap.add_argument("--codec-tile", type=int, default=0, help="codec tile bytes (experiments)")
     ap.add_argument("--codec-threads", type=int, default=0, help="codec threads per CTA (experiments)")
+    ap.add_argument("--codec-carveout", type=int, default=50, help="codec shared-memory carveout percent (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")

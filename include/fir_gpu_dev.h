@@ -46,9 +46,10 @@ FIR_GPU_API int fir_gpu_set_variant(fir_gpu_ctx *ctx, int variant);
 FIR_GPU_API int fir_gpu_variant_count(void);
 FIR_GPU_API const char *fir_gpu_variant_name(int variant);
 
-/* Tile size (interleaved bytes staged per trip) and threads per CTA (128 or 256) of the
- * PCM decode / encode kernels, for tuning sweeps; the result does not depend on them. */
-FIR_GPU_API int fir_gpu_set_codec_geometry(fir_gpu_ctx *ctx, int tile_bytes, int threads);
+/* Tile size (interleaved bytes staged per trip; 0 = the default of 4096 samples), threads per CTA (128 or 256) and shared-memory
+ * carveout (percent of the SM's array, -1 = the driver's choice) of the PCM decode / encode
+ * kernels, for tuning sweeps; the result does not depend on them. */
+FIR_GPU_API int fir_gpu_set_codec_geometry(fir_gpu_ctx *ctx, int tile_bytes, int threads, int smem_carveout_pct);
 
 /* Test hook: the next n fir_gpu_create calls fail after their streams, events and device
  * buffers exist (proves that a half-built context is torn down completely). */

@@ -100,7 +100,61 @@ def test_sample_block_mode_across_gpus_equals_single_gpu(tmp_path, oracle_mod):
     assert run("-g", 1, "-f", 20, "-s", 100, "-n", src, one).returncode == 0
     r = run("-g", 2, "-v", "-f", 20, "-s", 100, "-n", src, two)
     assert r.returncode == 0 and "sample blocks" in r.stdout
+    assert "ncclAllReduce(max)" in r.stdout            # the peak exchange is the NCCL collective north_star names
     assert one.read_bytes() == two.read_bytes()
+    # and without NCCL (the host max of the same scalars): same bytes
+    three = tmp_path / "three.wav"
+    r = subprocess.run([LOWCUT, "-g", "2", "-v", "-f", "20", "-s", "100", "-n", str(src), str(three)], capture_output=True,
+                       text=True, env=dict(os.environ, LOWCUT_NO_NCCL="1"))
+    assert r.returncode == 0 and "host max" in r.stdout
+    assert one.read_bytes() == three.read_bytes()
+
+
+def test_nccl_peak_allreduce_across_contexts_on_two_gpus(oracle_mod):
+    """fir_gpu_allreduce_peak: two blocks of one file on two devices of this process; after the
+    collective both contexts hold max(peak0, peak1) (ProcessFile.cp:92-96 over the whole file)."""
+    from audio_fir_filter_b200 import Context, capi, plan_blocks
+
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fs, ch, bits, frames = 8000, 2, 16, 100_000
+    pcm = oracle_mod.synth_pcm(11, 0, frames, ch, bits, True, fs)
+    ctxs = [Context(0), Context(1)]
+    capi.comm_prepare(ctxs)
+    peaks = []
+    fb = ch * bits // 8
+    for r, cx in enumerate(ctxs):
+        k = cx.build_kernel(40.0 / fs, 50.0 / fs)
+        b = plan_blocks(frames, 2, k.half_len)[r]
+        cx.apply(k, pcm[(b.start - b.halo_left) * fb:(b.start + b.frames + b.halo_right) * fb], b.frames, ch, bits, True,
+                 b.halo_left, b.halo_right)
+        peaks.append(cx.peak())
+    g = capi.allreduce_peak(ctxs)
+    assert g == max(peaks) and peaks[0] != peaks[1]
+    assert ctxs[0].peak() == g and ctxs[1].peak() == g
+    want = oracle_mod.process(pcm, frames, ch, bits, True, 40.0 / fs, 50.0 / fs, True)
+    assert abs(g - want["peak"]) <= 1e-12 * want["peak"]
+    for cx in ctxs:
+        cx.close()
+
+
+def test_batch_overwrite_with_one_basename_twice_last_input_wins(tmp_path, oracle_mod):
+    """-O with a/x.wav b/x.wav out/: the reference processes both in turn, the second replacing
+    the first's output (main.cp:143-146); here the clash is settled up front -- one job, the
+    later input -- instead of two lanes writing one file."""
+    fs, ch, bits, frames = 8000, 2, 16, 30_000
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    pa = oracle_mod.synth_pcm(1, 0, frames, ch, bits, False, fs).tobytes()
+    pb = oracle_mod.synth_pcm(2, 0, frames, ch, bits, False, fs).tobytes()
+    (tmp_path / "a" / "x.wav").write_bytes(wav_bytes(pa, ch, bits, fs))
+    db = wav_bytes(pb, ch, bits, fs)
+    (tmp_path / "b" / "x.wav").write_bytes(db)
+    out = tmp_path / "out"
+    r = run("-O", "-f", 40, "-s", 400, tmp_path / "a" / "x.wav", tmp_path / "b" / "x.wav", out)
+    assert r.returncode == 0, r.stderr
+    assert sorted(p.name for p in out.iterdir()) == ["x.wav"]
+    check_output(oracle_mod, db, (out / "x.wav").read_bytes(), pb, ch, bits, False, fs, 40.0, 400.0, False)
 
 
 def test_config1_full_size_file_through_the_cli(tmp_path, oracle_mod):

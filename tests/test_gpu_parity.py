@@ -720,3 +720,27 @@ def test_encode_saturates_like_the_oracle_for_absurd_gains(ctx, oracle_mod, bits
         want = oracle_mod.encode(y, scale, bits, False)
         assert np.array_equal(out, want), scale
     k.free()
+
+
+def test_peak_allreduce_entry_point_on_one_device(ctx, oracle_mod):
+    """fir_gpu_allreduce_peak with a single block is that block's peak (no collective); two blocks
+    on ONE device are refused -- a sample block per device is the contract."""
+    from audio_fir_filter_b200 import Context, capi
+
+    fs, frames, ch, bits = 8000, 20_000, 2, 16
+    pcm = oracle_mod.synth_pcm(3, 0, frames, ch, bits, False, fs)
+    k = ctx.build_kernel(40.0 / fs, 50.0 / fs)
+    ctx.apply(k, pcm, frames, ch, bits, False)
+    assert capi.allreduce_peak([ctx]) == ctx.peak()
+    other = Context(0)
+    other.apply(k, pcm, frames, ch, bits, False)
+    with pytest.raises(capi.FirGpuError) as e:
+        capi.allreduce_peak([ctx, other])
+    assert e.value.code in (capi.ERR_INVALID, capi.ERR_STATE)      # INVALID: same device (STATE only if NCCL is absent)
+    fresh = Context(0)
+    with pytest.raises(capi.FirGpuError) as e:
+        capi.allreduce_peak([fresh])
+    assert e.value.code == capi.ERR_STATE                            # nothing parked
+    fresh.close()
+    other.close()
+    k.free()

@@ -6,7 +6,8 @@ profiles/ (run here, no GPU needed):
                             -> profiles/fir_traffic.json      (dram read+write of that launch)
   gpurun_out/launches_*.csv -> profiles/<name>_launches*.{csv,txt}
 
-usage: python tools/refresh_profiles.py --rep gpurun_out/x.ncu-rep --cfg 2 --round r1
+usage: python tools/refresh_profiles.py --rep gpurun_out/x.ncu-rep --cfg 2 --round r2
+(tools/sass_evidence.py regenerates the SASS evidence from the shipped library)
 """
 import argparse
 import collections
@@ -16,18 +17,20 @@ import os
 import shutil
 import subprocess
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ap = argparse.ArgumentParser()
 ap.add_argument("--rep", default="")
 ap.add_argument("--launches", default="")
 ap.add_argument("--cfg", type=int, default=2)
-ap.add_argument("--round", default="r1")
+ap.add_argument("--round", default="r2")
+ap.add_argument("--name", default="fir_dmma", help="kernel tag in the output file name")
 a = ap.parse_args()
 P = os.path.join(ROOT, "profiles")
 
 if a.rep:
-    out = os.path.join(P, f"{a.round}_fir_dmma_cfg{a.cfg}_ncu.txt")
+    out = os.path.join(P, f"{a.round}_{a.name}_cfg{a.cfg}_ncu.txt")
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), a.rep], capture_output=True,
                          text=True).stdout
     open(out, "w").write(txt)
@@ -40,10 +43,16 @@ if a.rep:
         if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(p[1]) * mul[p[2]]
     tp = os.path.join(P, "fir_traffic.json")
+    if a.name != "fir_dmma":
+        print(out, tot)
+        sys.exit(0)
     d = json.load(open(tp)) if os.path.exists(tp) else {}
     d[f"cfg{a.cfg}"] = tot
     d["source"] = (f"profiles/{os.path.basename(out)} (ncu --set full, one launch of {kern} on bench.py's config "
-                   f"{a.cfg}): dram__bytes_read.sum + dram__bytes_write.sum")
+                   f"{a.cfg}, captured {time.strftime('%Y-%m-%d')}): dram__bytes_read.sum + dram__bytes_write.sum")
+    d["captured"] = time.strftime("%Y-%m-%d")
+    d["note"] = ("bench.py copies this constant into roofline.traffic and names this file in roofline.traffic_source; "
+                 "it is NOT re-measured by a bench run (a bench number is never taken under a profiler)")
     json.dump(d, open(tp, "w"), indent=1)
     print(out, tot)
 

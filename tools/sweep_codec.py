@@ -19,7 +19,8 @@ from bench import SEED, peak_hbm  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=400.0, help="PCM megabytes per pass")
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--geoms", default="8192x128,8192x256,16384x128,16384x256,24576x256,32768x256,49152x256")
+ap.add_argument("--geoms", default="0x256x50,8192x256x50,12288x256x50,16384x256x50,16384x128x50,32768x256x50,0x256x-1",
+                help="tile bytes x threads x shared-memory carveout percent (-1 = driver's choice)")
 a = ap.parse_args()
 FORMATS = [("cfg2 16BE x2", 2, 16, True, 44100), ("cfg1/4 24LE x2", 2, 24, False, 48000),
            ("cfg3 24LE x8", 8, 24, False, 96000), ("cfg5 32LE x16", 16, 32, False, 192000),
@@ -38,8 +39,8 @@ for name, ch, bits, be, fs in FORMATS:
     dec_bytes, enc_bytes = frames * fb + frames * ch * 8, frames * ch * 8 + frames * fb
     ref = None
     for g in a.geoms.split(","):
-        tile, nt = (int(v) for v in g.split("x"))
-        ctx.set_codec_geometry(tile, nt)
+        tile, nt, carve = (int(v) for v in (g.split("x") + ["50"])[:3])
+        ctx.set_codec_geometry(tile, nt, carve)
         dec, enc = [], []
         for _ in range(a.reps + 1):
             ctx.apply_dev(k, d_in, frames, ch, bits, be)
