@@ -231,8 +231,15 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		// Sample-block mode: the peak is one ncclAllReduce(max) over the blocks' device scalars.
 		// The communicator comes up on its own thread while the blocks are read and filtered.
 		std::vector<fir_gpu_ctx*> block_ctxs(ctxs.begin(), ctxs.begin() + (std::ptrdiff_t) world);
+		// Bringing an NCCL communicator up costs a second or so: it is worth its 8 bytes when the blocks
+		// filter for at least that long (the start-up hides under the FIR); a short file forced onto
+		// several GPUs takes the max of the n scalars on the host instead.  LOWCUT_NCCL=1 / 0 overrides.
+		const double block_seconds =
+			2.0 * (double) fir_gpu_kernel_num_taps(ks[0]) * (double) blocks[0].frames * l.channels / 35.0e12;
+		bool use_nccl = world > 1 && block_seconds >= 1.0;
+		if (const char* e = std::getenv("LOWCUT_NCCL")) use_nccl = world > 1 && std::atoi(e) != 0;
 		std::thread comm_up;
-		if (world > 1) comm_up = std::thread([&] { fir_gpu_comm_prepare(block_ctxs.data(), (int) world); });
+		if (use_nccl) comm_up = std::thread([&] { fir_gpu_comm_prepare(block_ctxs.data(), (int) world); });
 		std::vector<std::thread> th;
 		for (size_t r = 0; r < world; ++r)
 			th.emplace_back([&, r] {
@@ -262,13 +269,14 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				// (NCCL over NVLink, on the device scalars).  Without a loadable NCCL the n doubles that
 				// fir_gpu_peak already brought back are compared here instead.
 				const char* how = "single block";
-				if (world > 1 && !std::getenv("LOWCUT_NO_NCCL") &&
-				    fir_gpu_allreduce_peak(block_ctxs.data(), (int) world, &peak) == FIR_GPU_OK) {
+				if (use_nccl && fir_gpu_allreduce_peak(block_ctxs.data(), (int) world, &peak) == FIR_GPU_OK) {
 					how = "ncclAllReduce(max) over the blocks";
 					if (peak != *std::max_element(peaks.begin(), peaks.end()))
 						throw GpuError(FIR_GPU_ERR_STATE, "the all-reduced peak is not the max of the block peaks");
 				} else {
-					if (world > 1) how = "host max of the blocks' peaks (NCCL not used)";
+					if (world > 1)
+						how = use_nccl ? "host max of the blocks' peaks (NCCL could not be loaded)"
+						               : "host max of the blocks' peaks (blocks too short to hide an NCCL start-up; LOWCUT_NCCL=1 forces it)";
 					peak = *std::max_element(peaks.begin(), peaks.end());
 				}
 				status(std::format("  peak exchange: {}", how));
