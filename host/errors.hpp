@@ -35,6 +35,11 @@ struct FormatError : std::runtime_error {
 	using std::runtime_error::runtime_error;
 };
 
+// A worker process of the batch scenario failed; it has already reported why on stderr.
+struct BatchFailed : std::runtime_error {
+	BatchFailed() : std::runtime_error("") {}
+};
+
 struct GpuError : std::runtime_error {
 	int code;
 	GpuError(int code_, const std::string& what) : std::runtime_error(what), code(code_) {}

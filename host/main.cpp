@@ -105,17 +105,18 @@ int main(int argc, char** argv)
 				if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
 				jobs.emplace_back(in, out);
 			}
-			GpuPool pool(cli.gpus);
-			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
 			// existing destinations (-O) are replaced one by one, by the rename that completes each
 			// file (the reference removes each only when it reaches it, main.cp:144): if a file
-			// fails, the old outputs of the files that were not reached are still there
-			process_batch(jobs, opts, pool);
+			// fails, the old outputs of the files that were not reached are still there.
+			// Nothing has touched CUDA yet: process_batch may fork one worker process per GPU.
+			process_batch(jobs, opts, cli.gpus);
 			leave_now();
 		}
 	} catch (const StopNoError& e) {
 		const std::string s = e.what();
 		if (!s.empty()) std::cout << s << std::endl;
+	} catch (const BatchFailed&) {
+		exit_val = EXIT_FAILURE; // the worker process that failed has already said why
 	} catch (const std::exception& e) {
 		std::cerr << e.what() << std::endl;
 		exit_val = EXIT_FAILURE;

@@ -4,14 +4,18 @@
 #include <atomic>
 #include <barrier>
 #include <chrono>
+#include <cerrno>
 #include <cmath>
 #include <cstdlib>
+#include <new>
 #include <exception>
 #include <format>
 #include <iostream>
 #include <mutex>
 #include <thread>
 
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include "../include/fir_gpu.h"
@@ -410,18 +414,25 @@ static double estimate_file_seconds(const std::filesystem::path& p, const Filter
 	return fir_seconds(4.0 * l.sample_rate / opts.slope + 1.0, (double) l.frames, l.channels);
 }
 
-static size_t gpus_worth_starting(const GpuPool& pool, double seconds)
+// How many GPUs a job of `seconds` of FIR is worth.  A context costs ~0.25 s to bring up; with a
+// process per GPU (batch mode) they come up in parallel, inside one process (sample-block mode)
+// one after the other -- every extra GPU must then bring a good second of FIR with it.
+static size_t gpus_worth(size_t limit, double seconds, double seconds_per_extra_gpu)
+{
+	const double g = std::floor(seconds / seconds_per_extra_gpu);
+	return (size_t) std::clamp<double>(g, 1.0, (double) std::max<size_t>(limit, 1));
+}
+
+static size_t gpus_worth_starting(const GpuPool& pool, double seconds, double seconds_per_extra_gpu)
 {
 	if (pool.forced()) return pool.limit();
-	// every extra GPU should bring at least ~0.2 s of FIR with it (context start-up is of that order)
-	const double g = std::floor(seconds / 0.2);
-	return (size_t) std::clamp<double>(g, 1.0, (double) pool.limit());
+	return gpus_worth(pool.limit(), seconds, seconds_per_extra_gpu);
 }
 
 void process_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
                   const FilterOptions& opts, GpuPool& pool)
 {
-	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
+	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts), 1.0);
 	std::vector<size_t> slots;
 	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, 1, &slots);
 	if (opts.verbose) say(std::format("  [{:8.3f} s since start] {} GPU context(s) ready", uptime(), ctxs.size()));
@@ -433,7 +444,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 {
 	double seconds = 0.0;
 	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
-	const size_t gpus = std::min(gpus_worth_starting(pool, seconds), jobs.size());
+	const size_t gpus = std::min(gpus_worth_starting(pool, seconds, 0.2), jobs.size());
 	// several lanes per GPU: while one file filters, others read, upload, download, write.
 	// Per file the host side (page-cache read, output creation, write) costs a few times the
 	// FIR of a short file, so up to LANES files are in flight per GPU (LOWCUT_LANES overrides).
@@ -464,6 +475,136 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 	for (auto& t : th) t.join();
 	for (auto& e : errs)
 		if (e) std::rethrow_exception(e);
+}
+
+size_t visible_device_count_without_cuda(std::vector<std::string>* visible_ids)
+{
+	std::error_code ec;
+	size_t n = 0;
+	for (auto it = std::filesystem::directory_iterator("/proc/driver/nvidia/gpus", ec);
+	     !ec && it != std::filesystem::directory_iterator(); it.increment(ec))
+		++n;
+	std::vector<std::string> ids;
+	if (const char* e = std::getenv("CUDA_VISIBLE_DEVICES")) {
+		// the listed entries (ordinals or UUIDs), up to the first invalid one, as CUDA reads it
+		std::string s(e), item;
+		for (size_t i = 0; i <= s.size(); ++i) {
+			if (i == s.size() || s[i] == ',') {
+				if (item.empty()) break;
+				const bool ordinal = item.find_first_not_of("0123456789") == std::string::npos;
+				if (ordinal && (size_t) std::atoll(item.c_str()) >= n) break;
+				ids.push_back(item);
+				item.clear();
+			} else {
+				item += s[i];
+			}
+		}
+	} else {
+		for (size_t i = 0; i < n; ++i) ids.push_back(std::to_string(i));
+	}
+	if (n == 0) ids.clear();
+	if (visible_ids) *visible_ids = ids;
+	return ids.size();
+}
+
+namespace {
+
+// The page the worker processes of a batch share: the next job to hand out, and whether anybody failed.
+struct BatchShared {
+	std::atomic<size_t> next;
+	std::atomic<int> failed;
+};
+static_assert(std::atomic<size_t>::is_always_lock_free && std::atomic<int>::is_always_lock_free);
+
+// One worker process: the only device it sees is its own; up to LANES files in flight on it.
+[[noreturn]] void batch_worker(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
+                               const FilterOptions& opts, BatchShared* sh, size_t lanes)
+{
+	int code = EXIT_SUCCESS;
+	try {
+		GpuPool pool(1);
+		std::vector<size_t> slots;
+		const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(1, lanes, &slots);
+		std::vector<std::exception_ptr> errs(ctxs.size());
+		std::vector<std::thread> th;
+		for (size_t w = 0; w < ctxs.size(); ++w)
+			th.emplace_back([&, w] {
+				try {
+					for (size_t i = sh->next++; i < jobs.size() && !sh->failed; i = sh->next++)
+						run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, {slots[w]});
+				} catch (...) {
+					errs[w] = std::current_exception();
+					sh->failed = 1; // nobody starts another file (the reference stops at the first error, main.cp:157)
+				}
+			});
+		for (auto& t : th) t.join();
+		for (auto& e : errs)
+			if (e) std::rethrow_exception(e);
+	} catch (const std::exception& e) {
+		sh->failed = 1;
+		std::lock_guard<std::mutex> l(g_io);
+		std::cerr << e.what() << std::endl;
+		code = EXIT_FAILURE;
+	}
+	std::cout.flush();
+	std::cerr.flush();
+	std::_Exit(code); // the files are closed; tearing contexts down one by one buys nothing
+}
+
+} // namespace
+
+size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
+                     const FilterOptions& opts, unsigned want_gpus)
+{
+	double seconds = 0.0;
+	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
+	std::vector<std::string> ids;
+	const size_t n_dev = visible_device_count_without_cuda(&ids);
+	size_t gpus = want_gpus ? std::min<size_t>(want_gpus, std::max<size_t>(n_dev, 1)) : gpus_worth(n_dev, seconds, 0.2);
+	gpus = std::min(gpus, jobs.size());
+	if (n_dev == 0 || gpus <= 1 || std::getenv("LOWCUT_SINGLE_PROCESS")) {
+		// one GPU (or no way to count them without CUDA): everything in this process
+		GpuPool pool(n_dev == 0 ? want_gpus : (unsigned) std::max<size_t>(gpus, 1));
+		if (!opts.verbose) say(std::format("Using up to {} GPU(s).", pool.limit()));
+		process_batch(jobs, opts, pool);
+		return pool.limit();
+	}
+	if (!opts.verbose) say(std::format("Using up to {} GPU(s).", gpus));
+	size_t lanes = GpuPool::LANES;
+	if (const char* e = std::getenv("LOWCUT_LANES")) lanes = (size_t) std::max(1, std::atoi(e));
+	lanes = std::min(lanes, (jobs.size() + gpus - 1) / gpus);
+
+	void* page = ::mmap(nullptr, sizeof(BatchShared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+	if (page == MAP_FAILED) throw std::runtime_error("cannot map the batch's shared page");
+	BatchShared* sh = new (page) BatchShared{};
+	std::cout.flush();
+	std::cerr.flush();
+	std::vector<pid_t> kids;
+	for (size_t g = 0; g < gpus; ++g) {
+		const pid_t pid = ::fork();
+		if (pid < 0) {
+			sh->failed = 1;
+			break;
+		}
+		if (pid == 0) {
+			::setenv("CUDA_VISIBLE_DEVICES", ids[g].c_str(), 1); // before this process first touches CUDA
+			batch_worker(jobs, opts, sh, lanes);
+		}
+		kids.push_back(pid);
+	}
+	bool bad = kids.size() != gpus;
+	for (pid_t pid : kids) {
+		int st = 0;
+		while (::waitpid(pid, &st, 0) < 0 && errno == EINTR) {}
+		if (!WIFEXITED(st) || WEXITSTATUS(st) != EXIT_SUCCESS) {
+			if (WIFSIGNALED(st)) std::cerr << std::format("a GPU worker process died of signal {}", WTERMSIG(st)) << std::endl;
+			bad = true;
+		}
+	}
+	bad = bad || sh->failed;
+	::munmap(page, sizeof(BatchShared));
+	if (bad) throw BatchFailed();
+	return gpus;
 }
 
 } // namespace lowcut

@@ -6,6 +6,7 @@
 #pragma once
 #include <filesystem>
 #include <memory>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -69,11 +70,25 @@ private:
 void process_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
                   const FilterOptions& opts, GpuPool& pool);
 
-// Batch scenario (main.cp:132-147): whole files dealt to GPUs, one host worker
-// thread per device, no communication.  The first failure stops the hand-out of
-// further files and is rethrown once the files in flight are done.
+// Batch scenario (main.cp:132-147): whole files dealt to GPUs, no communication.  The first
+// failure stops the hand-out of further files and is rethrown once the files in flight are done.
+// This overload runs everything in the calling process (one context per lane and device).
 void process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
                    const FilterOptions& opts, GpuPool& pool);
+
+// The same, deciding itself how many GPUs are worth starting (want_gpus = 0) and -- when that is
+// more than one -- running ONE PROCESS PER GPU: the CUDA contexts then come up in parallel
+// (inside one process the driver creates them one after the other, ~0.5 s each on an 8-GPU box,
+// several times the FIR of a whole batch), and the files are handed out from a counter in shared
+// memory.  Must be called before anything in this process has touched CUDA.  Returns the number
+// of GPUs used.  Throws BatchFailed when a worker process failed (its message is already on stderr).
+size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
+                     const FilterOptions& opts, unsigned want_gpus);
+
+// NVIDIA devices this process may use, WITHOUT initialising CUDA (so that the answer can be had
+// before a fork): the entries of /proc/driver/nvidia/gpus, narrowed by CUDA_VISIBLE_DEVICES.
+// 0 = unknown (no such directory): callers fall back to asking CUDA.
+size_t visible_device_count_without_cuda(std::vector<std::string>* visible_ids = nullptr);
 
 // Seconds since the program was loaded (the -v time stamps; start-up cost is part of what a user waits for).
 double uptime();

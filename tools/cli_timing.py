@@ -22,7 +22,8 @@ from audio_fixtures import aiff_bytes, wav_bytes  # noqa: E402
 
 LOWCUT = os.path.join(ROOT, "host", "lowcut")
 subprocess.run(["make", "-C", os.path.join(ROOT, "host")], check=True, capture_output=True)
-GPUS = int(os.environ.get("GPUS", "0"))          # 0 = let lowcut choose
+GPUS = int(os.environ.get("GPUS", "0"))          # batch case only: -g GPUS (0 = let lowcut choose, as for the single files)
+ONLY = os.environ.get("ONLY", "")                # "batch": skip the single-file cases
 NB = int(os.environ.get("BATCH", "32"))
 REPS = int(os.environ.get("REPS", "3"))
 
@@ -35,8 +36,8 @@ def synth(seed, frames, ch, bits, be, rate):
         return d.cpu().numpy().tobytes()
 
 
-def timed(*args):
-    extra = ["-g", str(GPUS)] if GPUS else []
+def timed(*args, gpus=0):
+    extra = ["-g", str(gpus)] if gpus else []
     best = None
     for _ in range(REPS):
         t0 = time.perf_counter()
@@ -83,31 +84,35 @@ def report(name, wall, out, msamples):
 
 
 with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/dev/shm")) as d:
-    pcm = synth(3, 2_880_000, 2, 24, False, 48000)
-    w1 = os.path.join(d, "cfg1.wav")
-    open(w1, "wb").write(wav_bytes(pcm, 2, 24, 48000))
-    dt, out = timed("-v", "-f", 20, "-s", 20, w1, os.path.join(d, "cfg1_out.wav"))
-    report("cfg1: 60 s stereo 48 kHz 24-bit WAV, 9601 taps", dt, out, 5.76)
+    if ONLY != "batch":
+        pcm = synth(3, 2_880_000, 2, 24, False, 48000)
+        w1 = os.path.join(d, "cfg1.wav")
+        open(w1, "wb").write(wav_bytes(pcm, 2, 24, 48000))
+        dt, out = timed("-v", "-f", 20, "-s", 20, w1, os.path.join(d, "cfg1_out.wav"))
+        report("cfg1: 60 s stereo 48 kHz 24-bit WAV, 9601 taps", dt, out, 5.76)
 
-    pcm = synth(2, 26_460_000, 2, 16, True, 44100)
-    a = os.path.join(d, "cfg2.aif")
-    open(a, "wb").write(aiff_bytes(pcm, 2, 16, 44100.0))
-    dt, out = timed("-v", "-n", "-f", 30, "-s", 10, a, os.path.join(d, "cfg2_out.aif"))
-    report("cfg2: 10 min stereo 44.1 kHz 16-bit BE AIFF, -n, 17641 taps", dt, out, 52.92)
+        pcm = synth(2, 26_460_000, 2, 16, True, 44100)
+        a = os.path.join(d, "cfg2.aif")
+        open(a, "wb").write(aiff_bytes(pcm, 2, 16, 44100.0))
+        dt, out = timed("-v", "-n", "-f", 30, "-s", 10, a, os.path.join(d, "cfg2_out.aif"))
+        report("cfg2: 10 min stereo 44.1 kHz 16-bit BE AIFF, -n, 17641 taps", dt, out, 52.92)
 
     pcm = synth(1, 14_400_000, 2, 24, False, 48000)
     w = os.path.join(d, "cfg4.wav")
     open(w, "wb").write(wav_bytes(pcm, 2, 24, 48000))
-    dt, out = timed("-v", "-f", 20, "-s", 20, w, os.path.join(d, "cfg4_out.wav"))
-    report("cfg4: one 5 min stereo 48 kHz 24-bit WAV, 9601 taps", dt, out, 28.8)
+    if ONLY != "batch":
+        dt, out = timed("-v", "-f", 20, "-s", 20, w, os.path.join(d, "cfg4_out.wav"))
+        report("cfg4: one 5 min stereo 48 kHz 24-bit WAV, 9601 taps", dt, out, 28.8)
 
     files = []
     for i in range(NB):
         p = os.path.join(d, f"b{i}.wav")
         os.link(w, p)
         files.append(p)
-    dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"))
+    dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"), gpus=GPUS)
     m = re.search(r"Using up to (\d+) GPU", out)
-    print(json.dumps({"case": f"cfg4 batch: {NB} such files to a directory", "gpus": int(m.group(1)) if m else None,
+    g = int(m.group(1)) if m else 1
+    print(json.dumps({"case": f"cfg4 batch: {NB} such files ({NB * 86.4 / 1e3:.1f} GB in, as much out) to a directory",
+                      "gpus": g, "processes": "one per GPU" if g > 1 and not os.environ.get("LOWCUT_SINGLE_PROCESS") else "one",
                       "wall_s": round(dt, 3), "msamples_per_s_wall": round(NB * 28.8 / dt, 1),
-                      "fir_device_s_total": round(NB * 0.0153, 3)}), flush=True)
+                      "fir_device_s_per_gpu": round(NB * 0.0153 / g, 3)}), flush=True)
