@@ -992,7 +992,7 @@ def main() -> int:
             also[f"cfg{cid}"]["bench_seconds"] = time.perf_counter() - t0
             log(f"also cfg{cid}: {r['ms_per_step']:.1f} ms/step, {r['roofline']['achieved']:.2f} TFLOP/s, parity "
                 f"{r['parity']['ok'] if r['parity'] else 'skipped'} ({time.perf_counter() - t0:.1f} s)")
-    if also_mode != "none" and world == 8 and a.mode == "block":
+    if also_mode != "none" and world > 1 and a.mode == "block":   # auto: at N=8 only; --also all: at any N>1
         t0 = time.perf_counter()
         r = run_workload(env, 3, steps=1, warmup=1, strong=True, e2e_steps=1, e2e_warmup=0, parity=parity)
         also["cfg3_block_split"] = also_record(r)

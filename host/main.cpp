@@ -58,7 +58,8 @@ int main(int argc, char** argv)
 			if (fs::exists(out) && fs::equivalent(in, out))
 				throw UsageError("Input and output are the same file: " + in.string());
 			if (fs::exists(out) && !cli.overwrite) throw FileExists(out.string());
-			GpuPool pool(cli.gpus);
+			// decide how many GPUs this file is worth and hide the others from CUDA before it starts
+			GpuPool pool(restrict_devices_for_file(in, opts, cli.gpus));
 			// main.cp:69-72 prints its resource line only when -v is NOT given; kept as is
 			if (!opts.verbose) std::cout << std::format("Using up to {} GPU(s).", pool.limit()) << std::endl;
 			// the reference removes an existing output up front (main.cp:107); here the result is

@@ -215,6 +215,24 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 	double scale = 1.0, peak = 0.0;
 	int out_fd = -1;
 	if (l.frames > 0) {
+		// The output is created (every non-sample byte copied, ProcessFile.cp:104-112, and its pages
+		// allocated) on a thread of its own while the samples are read and filtered: it is a .part
+		// file until the result is complete, so nothing is lost by creating it before the peak is known.
+		std::exception_ptr out_err;
+		std::thread out_creator([&] {
+			try {
+				out_fd = in.create_output(part_path);
+			} catch (...) {
+				out_err = std::current_exception();
+			}
+		});
+		struct JoinOnExit {
+			std::thread& t;
+			~JoinOnExit()
+			{
+				if (t.joinable()) t.join();
+			}
+		} join_creator{out_creator};
 		std::vector<fir_gpu_kernel*> ks(world);
 		long long half_len = 0;
 		for (size_t r = 0; r < world; ++r) ks[r] = pool.kernel(slots[r], fc, bw, &half_len);
@@ -266,6 +284,11 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 			});
 		sync.arrive_and_wait();
 		if (comm_up.joinable()) comm_up.join();
+		out_creator.join(); // the output exists (or could not be created) before anything is decided about it
+		if (out_err) {
+			errs.push_back(out_err);
+			failed = true;
+		}
 		stamp("filtered, peak known");
 		try {
 			if (!failed) {
@@ -287,7 +310,6 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				scale = scale_for_peak(peak, opts.normalize);             // ProcessFile.cp:98-101
 				if (scale != 1.0) status("Doing audio normalize.");
 				status("Writing output file.");
-				out_fd = in.create_output(part_path);                     // every non-sample byte, verbatim
 			}
 		} catch (...) {
 			errs.push_back(std::current_exception());
@@ -304,7 +326,13 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 				std::filesystem::remove(part_path, ec); // never leave a half-written output behind
 				std::rethrow_exception(e);
 			}
-		std::filesystem::rename(part_path, output_path);
+		try {
+			std::filesystem::rename(part_path, output_path);
+		} catch (...) {
+			std::error_code ec;
+			std::filesystem::remove(part_path, ec); // never leave a .part behind, whatever went wrong
+			throw;
+		}
 		for (size_t r = 0; r < world; ++r) status(std::format("  GPU {}:{}", r, timing_line(ctxs[r])));
 	} else {
 		status("Writing output file.");
@@ -507,6 +535,19 @@ size_t visible_device_count_without_cuda(std::vector<std::string>* visible_ids)
 	return ids.size();
 }
 
+unsigned restrict_devices_for_file(const std::filesystem::path& input_path, const FilterOptions& opts, unsigned want_gpus)
+{
+	std::vector<std::string> ids;
+	const size_t n_dev = visible_device_count_without_cuda(&ids);
+	if (n_dev == 0) return want_gpus; // cannot tell without CUDA: the pool will ask it
+	const size_t world = want_gpus ? std::min<size_t>(want_gpus, n_dev)
+	                               : gpus_worth(n_dev, estimate_file_seconds(input_path, opts), 1.0);
+	std::string list;
+	for (size_t i = 0; i < world; ++i) list += (i ? "," : "") + ids[i];
+	::setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+	return (unsigned) world;
+}
+
 namespace {
 
 // The page the worker processes of a batch share: the next job to hand out, and whether anybody failed.
@@ -559,7 +600,22 @@ size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::fil
 	double seconds = 0.0;
 	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
 	std::vector<std::string> ids;
-	const size_t n_dev = visible_device_count_without_cuda(&ids);
+	size_t n_dev = visible_device_count_without_cuda(&ids);
+	if (const char* e = std::getenv("LOWCUT_WORKER_DEVICES")) {
+		// test hook: the CUDA_VISIBLE_DEVICES value of each worker process, e.g. "0,0" = two workers
+		// sharing one GPU (exercises the fork / shared-counter path on a one-GPU box)
+		ids.clear();
+		std::string s(e), item;
+		for (size_t i = 0; i <= s.size(); ++i) {
+			if (i == s.size() || s[i] == ',') {
+				if (!item.empty()) ids.push_back(item);
+				item.clear();
+			} else {
+				item += s[i];
+			}
+		}
+		n_dev = ids.size();
+	}
 	size_t gpus = want_gpus ? std::min<size_t>(want_gpus, std::max<size_t>(n_dev, 1)) : gpus_worth(n_dev, seconds, 0.2);
 	gpus = std::min(gpus, jobs.size());
 	if (n_dev == 0 || gpus <= 1 || std::getenv("LOWCUT_SINGLE_PROCESS")) {

@@ -85,6 +85,12 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
                      const FilterOptions& opts, unsigned want_gpus);
 
+// How many GPUs one file is worth (sample-block mode needs >= 1 s of FIR per extra GPU), decided
+// WITHOUT touching CUDA, and CUDA_VISIBLE_DEVICES narrowed to exactly those devices: cuInit then
+// initialises one device instead of eight (0.1 s instead of 0.6 s on an 8-GPU box -- more than
+// filtering a ten-minute file takes).  Returns the number to hand to GpuPool (0 = could not tell).
+unsigned restrict_devices_for_file(const std::filesystem::path& input_path, const FilterOptions& opts, unsigned want_gpus);
+
 // NVIDIA devices this process may use, WITHOUT initialising CUDA (so that the answer can be had
 // before a fork): the entries of /proc/driver/nvidia/gpus, narrowed by CUDA_VISIBLE_DEVICES.
 // 0 = unknown (no such directory): callers fall back to asking CUDA.

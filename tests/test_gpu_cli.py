@@ -197,3 +197,82 @@ def test_other_containers_end_to_end(tmp_path, oracle_mod, kind):
     r = run("-f", 25, "-s", 250, "-n", src, dst)
     assert r.returncode == 0, r.stderr
     check_output(oracle_mod, data, dst.read_bytes(), pcm, ch, bits, be, fs, 25.0, 250.0, True)
+
+
+def test_batch_mode_one_process_per_gpu_equals_one_gpu(tmp_path, oracle_mod):
+    """Batch scenario on several GPUs = one worker process per GPU pulling files from a shared
+    counter (main.cp:132-147 is a plain loop over independent files: no communication).  Same
+    bytes as on one GPU; a file that fails makes the run exit 1 with the reason on stderr once,
+    and leaves no .part file behind."""
+    from audio_fir_filter_b200 import capi
+
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fs, ch, bits = 48000, 2, 24
+    files = []
+    for i in range(7):
+        frames = 40_000 + 5_000 * i
+        pcm = oracle_mod.synth_pcm(100 + i, 0, frames, ch, bits, False, fs).tobytes()
+        p = tmp_path / f"in{i}.wav"
+        p.write_bytes(wav_bytes(pcm, ch, bits, fs))
+        files.append(p)
+    one, many = tmp_path / "one", tmp_path / "many"
+    r1 = run("-g", 1, "-f", 40, "-s", 400, *files, one)
+    assert r1.returncode == 0, r1.stderr
+    r2 = run("-g", 2, "-f", 40, "-s", 400, *files, many)
+    assert r2.returncode == 0, r2.stderr
+    assert "Using up to 2 GPU(s)." in r2.stdout
+    assert sorted(l for l in r2.stdout.splitlines() if l.startswith("Processing file:")) == \
+        sorted(f"Processing file: {p.name}" for p in files)
+    for p in files:
+        assert (one / p.name).read_bytes() == (many / p.name).read_bytes()
+    # one broken input: exit 1, its reason on stderr exactly once, nothing half-written left behind
+    bad = tmp_path / "broken.wav"
+    bad.write_bytes(b"RIFF\x04\0\0\0WAVE")
+    out3 = tmp_path / "third"
+    r3 = run("-g", 2, "-f", 40, "-s", 400, files[0], bad, files[1], files[2], out3)
+    assert r3.returncode == 1
+    assert r3.stderr.count("broken.wav") == 1, r3.stderr
+    assert not [p for p in out3.iterdir() if p.name.endswith(".part")]
+    # a failure INSIDE a worker process (the destination of one file is a directory: the rename that
+    # completes it fails): exit 1, reason on stderr, no .part left, the other workers stop handing out
+    out4 = tmp_path / "fourth"
+    (out4 / files[3].name).mkdir(parents=True)
+    r4 = run("-O", "-g", 2, "-f", 40, "-s", 400, *files, out4)
+    assert r4.returncode == 1 and files[3].name in r4.stderr, r4.stderr
+    assert not [p for p in out4.iterdir() if p.name.endswith(".part")]
+
+
+def test_batch_worker_processes_on_one_gpu(tmp_path, oracle_mod):
+    """The process-per-GPU batch path on a ONE-GPU box: LOWCUT_WORKER_DEVICES=0,0 (test hook) starts
+    two worker processes that share GPU 0 -- fork before CUDA, job counter and failure flag in
+    shared memory, each worker its own context.  Same bytes as the single-process run."""
+    fs, ch, bits = 48000, 2, 24
+    files = []
+    for i in range(9):
+        frames = 30_000 + 7_000 * i
+        pcm = oracle_mod.synth_pcm(200 + i, 0, frames, ch, bits, False, fs).tobytes()
+        p = tmp_path / f"w{i}.wav"
+        p.write_bytes(wav_bytes(pcm, ch, bits, fs))
+        files.append((p, pcm))
+    one, two = tmp_path / "one", tmp_path / "two"
+    r1 = subprocess.run([LOWCUT, "-f", "40", "-s", "400", *[str(p) for p, _ in files], str(one)], capture_output=True, text=True,
+                        env=dict(os.environ, LOWCUT_SINGLE_PROCESS="1"))
+    assert r1.returncode == 0, r1.stderr
+    r2 = subprocess.run([LOWCUT, "-g", "2", "-f", "40", "-s", "400", *[str(p) for p, _ in files], str(two)], capture_output=True,
+                        text=True, env=dict(os.environ, LOWCUT_WORKER_DEVICES="0,0"))
+    assert r2.returncode == 0, r2.stderr
+    assert "Using up to 2 GPU(s)." in r2.stdout
+    assert sorted(l for l in r2.stdout.splitlines() if l.startswith("Processing file:")) == \
+        sorted(f"Processing file: {p.name}" for p, _ in files)
+    for p, pcm in files:
+        assert (one / p.name).read_bytes() == (two / p.name).read_bytes()
+    p, pcm = files[4]
+    check_output(oracle_mod, p.read_bytes(), (two / p.name).read_bytes(), pcm, ch, bits, False, fs, 40.0, 400.0, False)
+    # a failure inside a worker: exit 1, the reason on stderr, no .part left
+    out3 = tmp_path / "three"
+    (out3 / files[2][0].name).mkdir(parents=True)
+    r3 = subprocess.run([LOWCUT, "-O", "-g", "2", "-f", "40", "-s", "400", *[str(p) for p, _ in files], str(out3)],
+                        capture_output=True, text=True, env=dict(os.environ, LOWCUT_WORKER_DEVICES="0,0"))
+    assert r3.returncode == 1 and files[2][0].name in r3.stderr, r3.stderr
+    assert not [q for q in out3.iterdir() if q.name.endswith(".part")]

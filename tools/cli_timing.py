@@ -109,6 +109,15 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/dev/shm")) a
         p = os.path.join(d, f"b{i}.wav")
         os.link(w, p)
         files.append(p)
+    # the ceiling of the file system itself: the same number of files and bytes, created by as many threads as
+    # lowcut has lanes (4 per GPU), doing nothing else
+    probe = os.path.join(d, "tmpfs_write_probe")
+    subprocess.run(["g++", "-O2", "-pthread", "-o", probe, os.path.join(ROOT, "tools", "tmpfs_write_probe.cpp")], check=True)
+    os.mkdir(os.path.join(d, "probe"))
+    ngpu = GPUS or capi.device_count()
+    for pre in (0, 1):
+        r = subprocess.run([probe, os.path.join(d, "probe"), str(4 * ngpu), str(NB), "86", str(pre)], capture_output=True, text=True)
+        print(r.stdout.strip(), flush=True)
     dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"), gpus=GPUS)
     m = re.search(r"Using up to (\d+) GPU", out)
     g = int(m.group(1)) if m else 1
