@@ -744,14 +744,13 @@ void fir_gpu_kernel_free(fir_gpu_kernel* k)
 
 // ------------------------------------------------------------------- apply
 
-// The chunks of one apply: [f0, f0+nf) output frames each.  Every chunk fits the decoded-input
-// budget.  From host memory (modes 1 and 3) the pass is cut into up to 8 chunks of WHOLE WAVES of
-// FIR CTAs (extra launches then add no partial-wave tails): the FIR starts after the first chunk's
-// bytes have landed and every later upload hides under the FIR before it -- any PCIe rate above
-// ~2 GB/s keeps up, also when eight ranks share the host and the previous file's download runs in the
-// other direction (one big "rest of the file" upload stalled the FIR there).  Mode 3 also encodes and
-// downloads each chunk speculatively.  A streamed apply (mode 2) is cut into ~16 chunks that start as
-// their bytes are fed.
+// The chunks of one apply: [f0, f0+nf) output frames each.  Every chunk fits the
+// decoded-input budget.  From host memory the first chunk is a short one, so that the
+// upload of everything else hides under its FIR (and under the FIRs that follow);
+// a streamed apply (feed by feed) is cut into ~16 chunks that start as their bytes land.
+// (Measured in round 2: cutting the host path into 8 whole-wave chunks instead costs 0.85 ms of a
+// 53 ms config-2 pass -- every kernel boundary drains and refills the SMs -- and only pays when
+// eight ranks share one host's PCIe; hosts that want the copies hidden keep two files in flight.)
 static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c, const FirVariant& v, int64_t frames,
                                                             int ch, int64_t n_taps,
                                                             int mode /*0 dev, 1 host, 2 stream, 3 host + speculative out*/)
@@ -760,23 +759,25 @@ static std::vector<std::pair<int64_t, int64_t>> plan_chunks(const fir_gpu_ctx* c
 	int64_t chunk = (c->x_budget_bytes / 8 / ch - (n_taps + 2 * MAX_KT)) / t_out * t_out;
 	if (chunk < t_out) chunk = t_out;
 	std::vector<std::pair<int64_t, int64_t>> out;
+	int64_t f0 = 0;
 	if (mode == 2 && frames >= 256 * t_out) chunk = std::min(chunk, round_up(frames / 16, t_out));
-	if (mode == 1 || mode == 3) {
-		// one chunk per ~2.5 ms of FIR (35 TFLOP/s), at most 8, each a whole number of full waves of CTAs
+	if (mode == 3) {
+		// speculative downloads: one chunk per ~2.5 ms of FIR (35 TFLOP/s), at most 8, each a whole
+		// number of full waves of CTAs so that the extra launches do not add partial-wave tails
 		const double est_ms = 2.0 * (double) n_taps * (double) frames * ch / 35.0e9;
 		const int64_t n = std::clamp<int64_t>((int64_t) (est_ms / 2.5), 1, 8);
 		const int64_t wave = (int64_t) c->sm_count * v.ctas_per_sm;
 		const int64_t bx_unit = std::max<int64_t>(1, wave / std::gcd<int64_t>(wave, ch)); // grid.x per whole waves
 		const int64_t bx = round_up((frames / n + t_out - 1) / t_out, bx_unit);
 		if (n > 1) chunk = std::min(chunk, bx * t_out);
-		else if (frames >= 256 * t_out) {
-			// too short to split into waves: at least a short first chunk, so the upload of the rest hides
-			const int64_t first = std::min(chunk, round_up(frames / 16, t_out));
-			out.emplace_back(0, first);
-		}
+		else mode = 1; // too short to split for the downloads: at least hide the upload
 	}
-	for (int64_t f0 = out.empty() ? 0 : out.back().second; f0 < frames; f0 += chunk)
-		out.emplace_back(f0, std::min(chunk, frames - f0));
+	if (mode == 1 && frames >= 256 * t_out) {
+		const int64_t first = std::min(chunk, round_up(frames / 16, t_out));
+		out.emplace_back(0, first);
+		f0 = first;
+	}
+	for (; f0 < frames; f0 += chunk) out.emplace_back(f0, std::min(chunk, frames - f0));
 	return out;
 }
 

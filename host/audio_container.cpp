@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <format>
 
@@ -243,7 +244,7 @@ int AudioContainer::create_output(const std::filesystem::path& out) const
 		// on tmpfs / the page cache, writing into pages that already exist is a plain copy, whereas
 		// every first touch of a fresh page is a fault -- measured 2x slower per thread and much worse
 		// when 32 lanes do it at once.  Best effort: file systems without fallocate just skip it.
-		(void) ::fallocate(fd, 0, 0, (off_t) size_);
+		if (!std::getenv("LOWCUT_NO_FALLOCATE")) (void) ::fallocate(fd, 0, 0, (off_t) size_);
 #endif
 		std::vector<unsigned char> buf(1u << 22);
 		auto copy = [&](uint64_t a, uint64_t b) {
