@@ -34,6 +34,43 @@ void say(const std::string& s)
 	std::cout << s << std::endl;
 }
 
+// LOWCUT_TRACE=1: where the host threads of this process spent their time, summed over all files
+// and lanes, printed once at the end (tools/cli_timing.py shows it next to the wall time).
+struct Trace {
+	enum Phase { Read, Feed, WaitFir, CreateOutput, EncodeDownload, Write, Open, N };
+	std::atomic<int64_t> ns[N] = {};
+	std::atomic<int64_t> files{0};
+	bool on = std::getenv("LOWCUT_TRACE") != nullptr;
+	static const char* name(int p)
+	{
+		static const char* n[N] = {"read file -> pinned", "feed (upload calls)", "wait for FIR / peak", "create output + allocate",
+		                           "encode + download", "write pinned -> file", "open + parse"};
+		return n[p];
+	}
+	void report()
+	{
+		if (!on || !files) return;
+		std::string s = std::format("  trace (pid {}, {} files, thread-seconds):", (long) ::getpid(), files.load());
+		for (int p = 0; p < N; ++p) s += std::format(" {} {:.3f};", name(p), (double) ns[p] * 1e-9);
+		std::lock_guard<std::mutex> l(g_io);
+		std::cout << s << std::endl;
+	}
+} g_trace;
+
+struct Timed {
+	Trace::Phase p;
+	std::chrono::steady_clock::time_point t0;
+	explicit Timed(Trace::Phase ph) : p(ph)
+	{
+		if (g_trace.on) t0 = std::chrono::steady_clock::now();
+	}
+	~Timed()
+	{
+		if (g_trace.on)
+			g_trace.ns[p] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+	}
+};
+
 void check(int rc, const char* what)
 {
 	if (rc != FIR_GPU_OK) throw GpuError(rc, std::format("{}: {}", what, fir_gpu_last_error()));
@@ -141,9 +178,14 @@ void filter_block(fir_gpu_ctx* ctx, const fir_gpu_kernel* k, const AudioContaine
 	int i = 0;
 	for (uint64_t off = 0; off < total; off += PIECE_BYTES, i ^= 1) {
 		const uint64_t n = std::min(PIECE_BYTES, total - off);
-		in.read_payload(first + off, n, bufs[i]);              // while the previous piece uploads / filters
+		{
+			Timed tt(Trace::Read);
+			in.read_payload(first + off, n, bufs[i]);          // while the previous piece uploads / filters
+		}
+		Timed tt(Trace::Feed);
 		check(fir_gpu_apply_feed(ctx, bufs[i], n), "fir_gpu_apply_feed");
 	}
+	Timed tt(Trace::WaitFir);
 	check(fir_gpu_apply_end(ctx), "fir_gpu_apply_end");
 	check(fir_gpu_peak(ctx, peak), "fir_gpu_peak");            // ProcessFile.cp:92-96; waits for the FIR
 }
@@ -162,11 +204,15 @@ void encode_block(fir_gpu_ctx* ctx, const PcmLayout& l, const Block& b, double s
 	int i = 0;
 	for (int64_t f = 0; f < b.frames; f += piece, i ^= 1) {
 		const int64_t n = std::min(piece, b.frames - f);
-		check(fir_gpu_encode_range(ctx, scale, f, n, bufs[i]), "fir_gpu_encode_range");
+		{
+			Timed tt(Trace::EncodeDownload);
+			check(fir_gpu_encode_range(ctx, scale, f, n, bufs[i]), "fir_gpu_encode_range");
+		}
 		if (writer.joinable()) writer.join(); // the other buffer is on its way to the file
 		if (werr) std::rethrow_exception(werr);
 		writer = std::thread([&, f, n, i] {
 			try {
+				Timed tt(Trace::Write);
 				AudioContainer::write_payload(out_fd, l, (uint64_t) (b.start + f) * fb, (uint64_t) n * fb, bufs[i]);
 			} catch (...) {
 				werr = std::current_exception();
@@ -192,7 +238,12 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 	};
 
 	status("Opening input file.");                                   // ProcessFile.cp:33-35
+	const auto t_open = std::chrono::steady_clock::now();
 	AudioContainer in(input_path);
+	if (g_trace.on) {
+		g_trace.ns[Trace::Open] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_open).count();
+		++g_trace.files;
+	}
 	const PcmLayout& l = in.pcm();
 	say("Processing file: " + input_path.filename().string());       // ProcessFile.cp:37 (unconditional)
 	status(std::format("  {} {} ch, {} bit {}, {} Hz, {} frames, {} chunks", in.type_name(), l.channels, l.bits,
@@ -221,6 +272,7 @@ void run_file(const std::filesystem::path& input_path, const std::filesystem::pa
 		std::exception_ptr out_err;
 		std::thread out_creator([&] {
 			try {
+				Timed tt(Trace::CreateOutput);
 				out_fd = in.create_output(part_path);
 			} catch (...) {
 				out_err = std::current_exception();
@@ -484,6 +536,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 	const size_t workers = std::min(ctxs.size(), jobs.size());
 	if (workers <= 1) {
 		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, {slots[0]});
+		g_trace.report();
 		return;
 	}
 	std::atomic<size_t> next{0};
@@ -501,6 +554,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 			}
 		});
 	for (auto& t : th) t.join();
+	g_trace.report();
 	for (auto& e : errs)
 		if (e) std::rethrow_exception(e);
 }
@@ -587,6 +641,7 @@ static_assert(std::atomic<size_t>::is_always_lock_free && std::atomic<int>::is_a
 		std::cerr << e.what() << std::endl;
 		code = EXIT_FAILURE;
 	}
+	g_trace.report();
 	std::cout.flush();
 	std::cerr.flush();
 	std::_Exit(code); // the files are closed; tearing contexts down one by one buys nothing

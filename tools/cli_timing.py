@@ -118,7 +118,11 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/dev/shm")) a
     for pre in (0, 1):
         r = subprocess.run([probe, os.path.join(d, "probe"), str(4 * ngpu), str(NB), "86", str(pre)], capture_output=True, text=True)
         print(r.stdout.strip(), flush=True)
+    os.environ["LOWCUT_TRACE"] = "1"        # per-process phase totals (thread-seconds) after the batch
     dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"), gpus=GPUS)
+    for l in out.splitlines():
+        if "trace (pid" in l:
+            print(l.strip(), flush=True)
     m = re.search(r"Using up to (\d+) GPU", out)
     g = int(m.group(1)) if m else 1
     print(json.dumps({"case": f"cfg4 batch: {NB} such files ({NB * 86.4 / 1e3:.1f} GB in, as much out) to a directory",
