@@ -566,6 +566,18 @@ size_t visible_device_count_without_cuda(std::vector<std::string>* visible_ids)
 	for (auto it = std::filesystem::directory_iterator("/proc/driver/nvidia/gpus", ec);
 	     !ec && it != std::filesystem::directory_iterator(); it.increment(ec))
 		++n;
+	if (n == 0) {
+		// containers often hide /proc/driver/nvidia but must expose the device nodes CUDA opens:
+		// /dev/nvidia0, /dev/nvidia1, ... (not nvidiactl, nvidia-uvm, ...)
+		ec.clear();
+		for (auto it = std::filesystem::directory_iterator("/dev", ec); !ec && it != std::filesystem::directory_iterator();
+		     it.increment(ec)) {
+			const std::string name = it->path().filename().string();
+			if (name.size() > 6 && name.compare(0, 6, "nvidia") == 0 &&
+			    name.find_first_not_of("0123456789", 6) == std::string::npos)
+				++n;
+		}
+	}
 	std::vector<std::string> ids;
 	if (const char* e = std::getenv("CUDA_VISIBLE_DEVICES")) {
 		// the listed entries (ordinals or UUIDs), up to the first invalid one, as CUDA reads it
@@ -681,6 +693,7 @@ size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::fil
 		return pool.limit();
 	}
 	if (!opts.verbose) say(std::format("Using up to {} GPU(s).", gpus));
+	if (opts.verbose || std::getenv("LOWCUT_TRACE")) say(std::format("  one worker process per GPU ({} processes)", gpus));
 	size_t lanes = GpuPool::LANES;
 	if (const char* e = std::getenv("LOWCUT_LANES")) lanes = (size_t) std::max(1, std::atoi(e));
 	lanes = std::min(lanes, (jobs.size() + gpus - 1) / gpus);

@@ -92,8 +92,9 @@ size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::fil
 unsigned restrict_devices_for_file(const std::filesystem::path& input_path, const FilterOptions& opts, unsigned want_gpus);
 
 // NVIDIA devices this process may use, WITHOUT initialising CUDA (so that the answer can be had
-// before a fork): the entries of /proc/driver/nvidia/gpus, narrowed by CUDA_VISIBLE_DEVICES.
-// 0 = unknown (no such directory): callers fall back to asking CUDA.
+// before a fork): the entries of /proc/driver/nvidia/gpus (or, where a container hides that, the
+// /dev/nvidia<N> device nodes), narrowed by CUDA_VISIBLE_DEVICES.  0 = unknown: callers fall back
+// to asking CUDA.
 size_t visible_device_count_without_cuda(std::vector<std::string>* visible_ids = nullptr);
 
 // Seconds since the program was loaded (the -v time stamps; start-up cost is part of what a user waits for).

@@ -126,6 +126,6 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/dev/shm")) a
     m = re.search(r"Using up to (\d+) GPU", out)
     g = int(m.group(1)) if m else 1
     print(json.dumps({"case": f"cfg4 batch: {NB} such files ({NB * 86.4 / 1e3:.1f} GB in, as much out) to a directory",
-                      "gpus": g, "processes": "one per GPU" if g > 1 and not os.environ.get("LOWCUT_SINGLE_PROCESS") else "one",
+                      "gpus": g, "processes": "one per GPU" if "one worker process per GPU" in out else "one",
                       "wall_s": round(dt, 3), "msamples_per_s_wall": round(NB * 28.8 / dt, 1),
                       "fir_device_s_per_gpu": round(NB * 0.0153 / g, 3)}), flush=True)
