@@ -623,13 +623,23 @@ struct BatchShared {
 };
 static_assert(std::atomic<size_t>::is_always_lock_free && std::atomic<int>::is_always_lock_free);
 
+constexpr int EXIT_NO_DEVICE = 3; // a worker that found no usable device (and so did nothing)
+
 // One worker process: the only device it sees is its own; up to LANES files in flight on it.
 [[noreturn]] void batch_worker(const std::vector<std::pair<std::filesystem::path, std::filesystem::path>>& jobs,
                                const FilterOptions& opts, BatchShared* sh, size_t lanes)
 {
 	int code = EXIT_SUCCESS;
 	try {
-		GpuPool pool(1);
+		std::unique_ptr<GpuPool> pool_ptr;
+		try {
+			pool_ptr = std::make_unique<GpuPool>(1);
+		} catch (const GpuError&) {
+			// this worker's device cannot be used (a device node that is not ours to open, a GPU that is
+			// not a B200): it has taken no job -- the other workers share out all of them
+			std::_Exit(EXIT_NO_DEVICE);
+		}
+		GpuPool& pool = *pool_ptr;
 		std::vector<size_t> slots;
 		const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(1, lanes, &slots);
 		std::vector<std::exception_ptr> errs(ctxs.size());
@@ -717,18 +727,24 @@ size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::fil
 		kids.push_back(pid);
 	}
 	bool bad = kids.size() != gpus;
+	size_t worked = 0;
 	for (pid_t pid : kids) {
 		int st = 0;
 		while (::waitpid(pid, &st, 0) < 0 && errno == EINTR) {}
-		if (!WIFEXITED(st) || WEXITSTATUS(st) != EXIT_SUCCESS) {
+		if (WIFEXITED(st) && WEXITSTATUS(st) == EXIT_SUCCESS) ++worked;
+		else if (WIFEXITED(st) && WEXITSTATUS(st) == EXIT_NO_DEVICE) continue; // did nothing, took nothing
+		else {
 			if (WIFSIGNALED(st)) std::cerr << std::format("a GPU worker process died of signal {}", WTERMSIG(st)) << std::endl;
 			bad = true;
 		}
 	}
 	bad = bad || sh->failed;
+	const bool all_done = sh->next.load() >= jobs.size();
 	::munmap(page, sizeof(BatchShared));
 	if (bad) throw BatchFailed();
-	return gpus;
+	if (worked == 0 || !all_done)
+		throw GpuError(FIR_GPU_ERR_NO_DEVICE, "no usable B200 (sm_100) device; lowcut has no CPU path");
+	return worked;
 }
 
 } // namespace lowcut

@@ -269,6 +269,17 @@ def test_batch_worker_processes_on_one_gpu(tmp_path, oracle_mod):
         assert (one / p.name).read_bytes() == (two / p.name).read_bytes()
     p, pcm = files[4]
     check_output(oracle_mod, p.read_bytes(), (two / p.name).read_bytes(), pcm, ch, bits, False, fs, 40.0, 400.0, False)
+    # a worker whose device cannot be used (ordinal 99 does not exist) steps aside; the other one does every file
+    four = tmp_path / "four"
+    r4 = subprocess.run([LOWCUT, "-g", "2", "-f", "40", "-s", "400", *[str(p) for p, _ in files], str(four)], capture_output=True,
+                        text=True, env=dict(os.environ, LOWCUT_WORKER_DEVICES="0,99"))
+    assert r4.returncode == 0, r4.stderr
+    for p, _ in files:
+        assert (one / p.name).read_bytes() == (four / p.name).read_bytes()
+    # no worker with a usable device at all: the run fails loudly (no CPU path)
+    r5 = subprocess.run([LOWCUT, "-g", "2", "-f", "40", "-s", "400", *[str(p) for p, _ in files], str(tmp_path / "five")],
+                        capture_output=True, text=True, env=dict(os.environ, LOWCUT_WORKER_DEVICES="98,99"))
+    assert r5.returncode == 1 and "no CPU path" in r5.stderr
     # a failure inside a worker: exit 1, the reason on stderr, no .part left
     out3 = tmp_path / "three"
     (out3 / files[2][0].name).mkdir(parents=True)
