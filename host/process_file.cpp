@@ -40,6 +40,7 @@ struct Trace {
 	enum Phase { Read, Feed, WaitFir, CreateOutput, EncodeDownload, Write, Open, N };
 	std::atomic<int64_t> ns[N] = {};
 	std::atomic<int64_t> files{0};
+	double t_fork = 0.0, t_ready = 0.0; // seconds since program start: this worker forked / its contexts were up
 	bool on = std::getenv("LOWCUT_TRACE") != nullptr;
 	static const char* name(int p)
 	{
@@ -50,7 +51,8 @@ struct Trace {
 	void report()
 	{
 		if (!on || !files) return;
-		std::string s = std::format("  trace (pid {}, {} files, thread-seconds):", (long) ::getpid(), files.load());
+		std::string s = std::format("  trace (pid {}, {} files; forked at {:.3f} s, contexts ready at {:.3f} s, done at {:.3f} s; "
+		                            "thread-seconds):", (long) ::getpid(), files.load(), t_fork, t_ready, uptime());
 		for (int p = 0; p < N; ++p) s += std::format(" {} {:.3f};", name(p), (double) ns[p] * 1e-9);
 		std::lock_guard<std::mutex> l(g_io);
 		std::cout << s << std::endl;
@@ -533,6 +535,7 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 	std::vector<size_t> slots;
 	const std::vector<fir_gpu_ctx*> ctxs =
 		pool.acquire(gpus, std::min(lanes, (jobs.size() + gpus - 1) / gpus), &slots);
+	g_trace.t_ready = uptime();
 	const size_t workers = std::min(ctxs.size(), jobs.size());
 	if (workers <= 1) {
 		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, {slots[0]});
@@ -630,6 +633,7 @@ constexpr int EXIT_NO_DEVICE = 3; // a worker that found no usable device (and s
                                const FilterOptions& opts, BatchShared* sh, size_t lanes)
 {
 	int code = EXIT_SUCCESS;
+	g_trace.t_fork = uptime();
 	try {
 		std::unique_ptr<GpuPool> pool_ptr;
 		try {
@@ -642,6 +646,7 @@ constexpr int EXIT_NO_DEVICE = 3; // a worker that found no usable device (and s
 		GpuPool& pool = *pool_ptr;
 		std::vector<size_t> slots;
 		const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(1, lanes, &slots);
+		g_trace.t_ready = uptime();
 		std::vector<std::exception_ptr> errs(ctxs.size());
 		std::vector<std::thread> th;
 		for (size_t w = 0; w < ctxs.size(); ++w)
