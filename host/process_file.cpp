@@ -451,6 +451,29 @@ std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, size_t subs, std::v
 	return out;
 }
 
+std::vector<fir_gpu_ctx*> GpuPool::acquire_device(size_t device, size_t subs, std::vector<size_t>* slots)
+{
+	device = std::min(device, ordinals_.size() - 1);
+	subs = std::clamp<size_t>(subs, 1, LANES);
+	std::vector<size_t> want;
+	for (size_t sub = 0; sub < subs; ++sub) want.push_back(LANES * device + sub);
+	std::vector<std::thread> th;
+	std::vector<std::string> errs(lanes_.size());
+	for (size_t slot : want)
+		if (!lanes_[slot].ctx)
+			th.emplace_back([this, slot, &errs] {
+				if (fir_gpu_create(ordinals_[slot / LANES], &lanes_[slot].ctx) != FIR_GPU_OK) errs[slot] = fir_gpu_last_error();
+			});
+	for (auto& t : th) t.join();
+	std::vector<fir_gpu_ctx*> out;
+	for (size_t slot : want) {
+		if (!lanes_[slot].ctx) throw GpuError(FIR_GPU_ERR_NO_DEVICE, "cannot create a GPU context: " + errs[slot]);
+		out.push_back(lanes_[slot].ctx);
+	}
+	if (slots) *slots = want;
+	return out;
+}
+
 fir_gpu_kernel* GpuPool::kernel(size_t slot, double fc, double bw, long long* half_len)
 {
 	Lane& l = lanes_.at(slot); // a lane is used by one thread at a time: no lock
@@ -496,25 +519,30 @@ static double estimate_file_seconds(const std::filesystem::path& p, const Filter
 	return fir_seconds(4.0 * l.sample_rate / opts.slope + 1.0, (double) l.frames, l.channels);
 }
 
-// How many GPUs a job of `seconds` of FIR is worth.  A context costs ~0.25 s to bring up; with a
-// process per GPU (batch mode) they come up in parallel, inside one process (sample-block mode)
-// one after the other -- every extra GPU must then bring a good second of FIR with it.
-static size_t gpus_worth(size_t limit, double seconds, double seconds_per_extra_gpu)
+// How many GPUs a job of `seconds` of FIR is worth.  Every GPU a run touches costs about half a
+// second of wall time that no parallelism buys back: the driver creates (and, at exit, destroys)
+// contexts one after the other, machine-wide -- measured on the 8-GPU box: 0.26 s + 0.24 s per
+// device, in one process or in eight.  With g GPUs a job takes about seconds/g + GPU_COST*g, least
+// at g = sqrt(seconds / GPU_COST): 8 GPUs from ~30 s of FIR upwards (config 3: 29 s), 3 for the
+// 256-file batch of config 4 (3.9 s), 1 for a ten-minute file.
+constexpr double GPU_COST_SECONDS = 0.5;
+
+static size_t gpus_worth(size_t limit, double seconds)
 {
-	const double g = std::floor(seconds / seconds_per_extra_gpu);
+	const double g = std::round(std::sqrt(std::max(seconds, 0.0) / GPU_COST_SECONDS));
 	return (size_t) std::clamp<double>(g, 1.0, (double) std::max<size_t>(limit, 1));
 }
 
-static size_t gpus_worth_starting(const GpuPool& pool, double seconds, double seconds_per_extra_gpu)
+static size_t gpus_worth_starting(const GpuPool& pool, double seconds)
 {
 	if (pool.forced()) return pool.limit();
-	return gpus_worth(pool.limit(), seconds, seconds_per_extra_gpu);
+	return gpus_worth(pool.limit(), seconds);
 }
 
 void process_file(const std::filesystem::path& input_path, const std::filesystem::path& output_path,
                   const FilterOptions& opts, GpuPool& pool)
 {
-	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts), 1.0);
+	const size_t world = gpus_worth_starting(pool, estimate_file_seconds(input_path, opts));
 	std::vector<size_t> slots;
 	const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(world, 1, &slots);
 	if (opts.verbose) say(std::format("  [{:8.3f} s since start] {} GPU context(s) ready", uptime(), ctxs.size()));
@@ -526,36 +554,43 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 {
 	double seconds = 0.0;
 	for (const auto& j : jobs) seconds += estimate_file_seconds(j.first, opts);
-	const size_t gpus = std::min(gpus_worth_starting(pool, seconds, 0.2), jobs.size());
+	const size_t gpus = std::min(gpus_worth_starting(pool, seconds), jobs.size());
 	// several lanes per GPU: while one file filters, others read, upload, download, write.
 	// Per file the host side (page-cache read, output creation, write) costs a few times the
 	// FIR of a short file, so up to LANES files are in flight per GPU (LOWCUT_LANES overrides).
 	size_t lanes = GpuPool::LANES;
 	if (const char* e = std::getenv("LOWCUT_LANES")) lanes = (size_t) std::max(1, std::atoi(e));
-	std::vector<size_t> slots;
-	const std::vector<fir_gpu_ctx*> ctxs =
-		pool.acquire(gpus, std::min(lanes, (jobs.size() + gpus - 1) / gpus), &slots);
-	g_trace.t_ready = uptime();
-	const size_t workers = std::min(ctxs.size(), jobs.size());
-	if (workers <= 1) {
-		for (const auto& j : jobs) run_file(j.first, j.second, opts, pool, {ctxs[0]}, {slots[0]});
-		g_trace.report();
-		return;
-	}
+	lanes = std::min(lanes, (jobs.size() + gpus - 1) / gpus);
 	std::atomic<size_t> next{0};
 	std::atomic<bool> failed{false};
-	std::vector<std::exception_ptr> errs(workers);
+	std::mutex err_mutex;
+	std::vector<std::exception_ptr> errs;
 	std::vector<std::thread> th;
-	for (size_t w = 0; w < workers; ++w)
-		th.emplace_back([&, w] {
-			try {
-				for (size_t i = next++; i < jobs.size() && !failed; i = next++)
-					run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, {slots[w]});
-			} catch (...) {
-				errs[w] = std::current_exception();
-				failed = true;
-			}
-		});
+	auto lane_loop = [&](fir_gpu_ctx* ctx, size_t slot) {
+		try {
+			for (size_t i = next++; i < jobs.size() && !failed; i = next++)
+				run_file(jobs[i].first, jobs[i].second, opts, pool, {ctx}, {slot});
+		} catch (...) {
+			std::lock_guard<std::mutex> l(err_mutex);
+			errs.push_back(std::current_exception());
+			failed = true;
+		}
+	};
+	// The driver brings contexts up one device after the other anyway: do it in that order and let
+	// each device's lanes start on the files as soon as THEIR context exists, instead of waiting
+	// for the last device (2 s later on an 8-GPU box).
+	try {
+		for (size_t d = 0; d < gpus && !failed && next < jobs.size(); ++d) {
+			std::vector<size_t> slots;
+			const std::vector<fir_gpu_ctx*> ctxs = pool.acquire_device(d, lanes, &slots);
+			if (d == 0) g_trace.t_ready = uptime();
+			for (size_t w = 0; w < ctxs.size(); ++w) th.emplace_back(lane_loop, ctxs[w], slots[w]);
+		}
+	} catch (...) {
+		std::lock_guard<std::mutex> l(err_mutex);
+		errs.push_back(std::current_exception());
+		failed = true;
+	}
 	for (auto& t : th) t.join();
 	g_trace.report();
 	for (auto& e : errs)
@@ -610,7 +645,7 @@ unsigned restrict_devices_for_file(const std::filesystem::path& input_path, cons
 	const size_t n_dev = visible_device_count_without_cuda(&ids);
 	if (n_dev == 0) return want_gpus; // cannot tell without CUDA: the pool will ask it
 	const size_t world = want_gpus ? std::min<size_t>(want_gpus, n_dev)
-	                               : gpus_worth(n_dev, estimate_file_seconds(input_path, opts), 1.0);
+	                               : gpus_worth(n_dev, estimate_file_seconds(input_path, opts));
 	std::string list;
 	for (size_t i = 0; i < world; ++i) list += (i ? "," : "") + ids[i];
 	::setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
@@ -698,7 +733,7 @@ size_t process_batch(const std::vector<std::pair<std::filesystem::path, std::fil
 		}
 		n_dev = ids.size();
 	}
-	size_t gpus = want_gpus ? std::min<size_t>(want_gpus, std::max<size_t>(n_dev, 1)) : gpus_worth(n_dev, seconds, 0.2);
+	size_t gpus = want_gpus ? std::min<size_t>(want_gpus, std::max<size_t>(n_dev, 1)) : gpus_worth(n_dev, seconds);
 	gpus = std::min(gpus, jobs.size());
 	if (n_dev == 0 || gpus <= 1 || std::getenv("LOWCUT_SINGLE_PROCESS")) {
 		// one GPU (or no way to count them without CUDA): everything in this process

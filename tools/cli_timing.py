@@ -119,13 +119,17 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("TIMING_DIR", "/dev/shm")) a
         r = subprocess.run([probe, os.path.join(d, "probe"), str(4 * ngpu), str(NB), "86", str(pre)], capture_output=True, text=True)
         print(r.stdout.strip(), flush=True)
     os.environ["LOWCUT_TRACE"] = "1"        # per-process phase totals (thread-seconds) after the batch
-    dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"), gpus=GPUS)
-    for l in out.splitlines():
-        if "trace (pid" in l:
-            print(l.strip(), flush=True)
-    m = re.search(r"Using up to (\d+) GPU", out)
-    g = int(m.group(1)) if m else 1
-    print(json.dumps({"case": f"cfg4 batch: {NB} such files ({NB * 86.4 / 1e3:.1f} GB in, as much out) to a directory",
-                      "gpus": g, "processes": "one per GPU" if "one worker process per GPU" in out else "one",
-                      "wall_s": round(dt, 3), "msamples_per_s_wall": round(NB * 28.8 / dt, 1),
-                      "fir_device_s_per_gpu": round(NB * 0.0153 / g, 3)}), flush=True)
+    # lowcut's own choice of GPUs first (sqrt(FIR seconds / 0.5 s per GPU)), then every count asked for in GPUS_SWEEP
+    sweep = [GPUS] + [int(v) for v in os.environ.get("GPUS_SWEEP", "").split(",") if v]
+    for want in sweep:
+        dt, out = timed("-f", 20, "-s", 20, *files, os.path.join(d, "outdir"), gpus=want)
+        for l in out.splitlines():
+            if "trace (pid" in l:
+                print(l.strip(), flush=True)
+        m = re.search(r"Using up to (\d+) GPU", out)
+        g = int(m.group(1)) if m else 1
+        print(json.dumps({"case": f"cfg4 batch: {NB} such files ({NB * 86.4 / 1e3:.1f} GB in, as much out) to a directory",
+                          "gpus": g, "chosen_by": "lowcut" if not want else f"-g {want}",
+                          "processes": "one per GPU" if "one worker process per GPU" in out else "one",
+                          "wall_s": round(dt, 3), "msamples_per_s_wall": round(NB * 28.8 / dt, 1),
+                          "fir_device_s_per_gpu": round(NB * 0.0153 / g, 3)}), flush=True)
