@@ -451,6 +451,14 @@ std::vector<fir_gpu_ctx*> GpuPool::acquire(size_t n_devices, size_t subs, std::v
 	return out;
 }
 
+fir_gpu_ctx* GpuPool::acquire_slot(size_t slot)
+{
+	Lane& l = lanes_.at(slot); // a lane belongs to one thread: no lock
+	if (!l.ctx && fir_gpu_create(ordinals_[slot / LANES], &l.ctx) != FIR_GPU_OK)
+		throw GpuError(FIR_GPU_ERR_NO_DEVICE, std::string("cannot create a GPU context: ") + fir_gpu_last_error());
+	return l.ctx;
+}
+
 std::vector<fir_gpu_ctx*> GpuPool::acquire_device(size_t device, size_t subs, std::vector<size_t>* slots)
 {
 	device = std::min(device, ordinals_.size() - 1);
@@ -560,14 +568,20 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 	// FIR of a short file, so up to LANES files are in flight per GPU (LOWCUT_LANES overrides).
 	size_t lanes = GpuPool::LANES;
 	if (const char* e = std::getenv("LOWCUT_LANES")) lanes = (size_t) std::max(1, std::atoi(e));
-	lanes = std::min(lanes, (jobs.size() + gpus - 1) / gpus);
+	lanes = std::clamp<size_t>(std::min(lanes, (jobs.size() + gpus - 1) / gpus), 1, GpuPool::LANES);
 	std::atomic<size_t> next{0};
 	std::atomic<bool> failed{false};
 	std::mutex err_mutex;
 	std::vector<std::exception_ptr> errs;
 	std::vector<std::thread> th;
-	auto lane_loop = [&](fir_gpu_ctx* ctx, size_t slot) {
+	// Every lane is a thread that brings up ITS context and then pulls files: the first lane that
+	// exists starts filtering while the driver is still creating the others (it creates contexts
+	// one after the other: 4 lanes on one device took 1.4 s to be "all ready", the first 0.3 s).
+	std::atomic<bool> first_ready{false};
+	auto lane_loop = [&](size_t slot) {
 		try {
+			fir_gpu_ctx* ctx = pool.acquire_slot(slot);
+			if (!first_ready.exchange(true)) g_trace.t_ready = uptime();
 			for (size_t i = next++; i < jobs.size() && !failed; i = next++)
 				run_file(jobs[i].first, jobs[i].second, opts, pool, {ctx}, {slot});
 		} catch (...) {
@@ -576,21 +590,8 @@ void process_batch(const std::vector<std::pair<std::filesystem::path, std::files
 			failed = true;
 		}
 	};
-	// The driver brings contexts up one device after the other anyway: do it in that order and let
-	// each device's lanes start on the files as soon as THEIR context exists, instead of waiting
-	// for the last device (2 s later on an 8-GPU box).
-	try {
-		for (size_t d = 0; d < gpus && !failed && next < jobs.size(); ++d) {
-			std::vector<size_t> slots;
-			const std::vector<fir_gpu_ctx*> ctxs = pool.acquire_device(d, lanes, &slots);
-			if (d == 0) g_trace.t_ready = uptime();
-			for (size_t w = 0; w < ctxs.size(); ++w) th.emplace_back(lane_loop, ctxs[w], slots[w]);
-		}
-	} catch (...) {
-		std::lock_guard<std::mutex> l(err_mutex);
-		errs.push_back(std::current_exception());
-		failed = true;
-	}
+	for (size_t sub = 0; sub < lanes; ++sub) // lane 0 of every device first, then the second lanes, ...
+		for (size_t d = 0; d < gpus; ++d) th.emplace_back(lane_loop, GpuPool::LANES * d + sub);
 	for (auto& t : th) t.join();
 	g_trace.report();
 	for (auto& e : errs)
@@ -679,16 +680,17 @@ constexpr int EXIT_NO_DEVICE = 3; // a worker that found no usable device (and s
 			std::_Exit(EXIT_NO_DEVICE);
 		}
 		GpuPool& pool = *pool_ptr;
-		std::vector<size_t> slots;
-		const std::vector<fir_gpu_ctx*> ctxs = pool.acquire(1, lanes, &slots);
-		g_trace.t_ready = uptime();
-		std::vector<std::exception_ptr> errs(ctxs.size());
+		lanes = std::clamp<size_t>(lanes, 1, GpuPool::LANES);
+		std::vector<std::exception_ptr> errs(lanes);
 		std::vector<std::thread> th;
-		for (size_t w = 0; w < ctxs.size(); ++w)
+		std::atomic<bool> first_ready{false};
+		for (size_t w = 0; w < lanes; ++w)
 			th.emplace_back([&, w] {
 				try {
+					fir_gpu_ctx* ctx = pool.acquire_slot(w); // this lane's context; the lanes that exist already work
+					if (!first_ready.exchange(true)) g_trace.t_ready = uptime();
 					for (size_t i = sh->next++; i < jobs.size() && !sh->failed; i = sh->next++)
-						run_file(jobs[i].first, jobs[i].second, opts, pool, {ctxs[w]}, {slots[w]});
+						run_file(jobs[i].first, jobs[i].second, opts, pool, {ctx}, {w});
 				} catch (...) {
 					errs[w] = std::current_exception();
 					sh->failed = 1; // nobody starts another file (the reference stops at the first error, main.cp:157)

@@ -41,8 +41,10 @@ public:
 	// parallel on demand.
 	static constexpr size_t LANES = 4;
 	std::vector<fir_gpu_ctx*> acquire(size_t n_devices, size_t subs, std::vector<size_t>* slots = nullptr);
-	// The lanes of ONE device (batch mode brings devices up one after the other and starts each
-	// device's lanes as soon as they exist).
+	// One lane's context, created by the thread that will use it (batch mode: every lane brings up
+	// its own context and starts on the files at once; the others are still being created).
+	fir_gpu_ctx* acquire_slot(size_t slot);
+	// The lanes of ONE device.
 	std::vector<fir_gpu_ctx*> acquire_device(size_t device, size_t subs, std::vector<size_t>* slots = nullptr);
 	// Two pinned buffers of `bytes` for upload and two for download, per lane, reused across files.
 	unsigned char* staging(size_t slot, int which /*0..3*/, size_t bytes);
