@@ -21,6 +21,7 @@ ap.add_argument("--mb", type=float, default=400.0, help="PCM megabytes per pass"
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--geoms", default="0x256x50,8192x256x50,12288x256x50,16384x256x50,16384x128x50,32768x256x50,0x256x-1",
                 help="tile bytes x threads x shared-memory carveout percent (-1 = driver's choice)")
+ap.add_argument("--formats", default="", help="comma-separated substrings of the format names to run (default: all)")
 a = ap.parse_args()
 FORMATS = [("cfg2 16BE x2", 2, 16, True, 44100), ("cfg1/4 24LE x2", 2, 24, False, 48000),
            ("cfg3 24LE x8", 8, 24, False, 96000), ("cfg5 32LE x16", 16, 32, False, 192000),
@@ -30,6 +31,8 @@ k = ctx.kernel_from_taps(np.array([1.0]))
 peak = peak_hbm()
 best = {}
 for name, ch, bits, be, fs in FORMATS:
+    if a.formats and not any(s in name for s in a.formats.split(",")):
+        continue
     fb = ch * bits // 8
     frames = int(a.mb * 1e6 / fb) & ~1023
     d_in = torch.empty(frames * fb, dtype=torch.uint8, device="cuda:0")
