@@ -453,10 +453,13 @@ class Env:
         if a.codec_tile or a.codec_threads or a.codec_carveout != 50:
             self.ctx.set_codec_geometry(a.codec_tile, a.codec_threads or 256, a.codec_carveout)
         self._ctx2 = None
-        # measured FP64 ceilings of this GPU, before the run (register-resident probes)
-        self.dfma_peak = self.ctx.fp64_peak(0, 0.25)
-        self.dmma_peak = self.ctx.fp64_peak(1, 0.25)
-        self.clock_note = None
+        # measured FP64 ceilings of this GPU, before the run (register-resident probes), with the
+        # clocks the GPU ran at while they were measured (they are the roofline's denominator)
+        sampler = ClockSampler(self.local) if self.rank == 0 else None
+        t0 = time.perf_counter()
+        self.dfma_peak = self.ctx.fp64_peak(0, 0.4)
+        self.dmma_peak = self.ctx.fp64_peak(1, 0.4)
+        self.probe_clocks = sampler.stop(t0, time.perf_counter()) if sampler else None
 
     @property
     def ctx2(self):
@@ -796,7 +799,7 @@ def run_workload(env: Env, cfg_id: int, *, steps: int, warmup: int, mode: str = 
                        + ("DMMA m8n8k4 f64 probe" if is_dmma else "DFMA probe")
                        + " (fir_gpu_fp64_peak); MEASURED_PEAKS.json has no FP64 figure (its bf16 number is for "
                          "tcgen05, which has no FP64 kind)",
-        "dfma_probe": env.dfma_peak,
+        "dfma_probe": env.dfma_peak, "probe_clocks": env.probe_clocks,
         "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12, "dmma_probe": env.dmma_peak,
         "frac_of_nominal": achieved / (148 * 64 * 2 * 1.965e9 / 1e12),
         "flop_per_launch": flop_launch, "fir_ms_per_launch": fir_avg_ms,
@@ -853,6 +856,84 @@ def wav_file_bytes(pcm: bytes, channels: int, bits: int, rate: int) -> bytes:
     body = chunk(b"fmt ", struct.pack("<HHIIHH", 1, channels, rate, rate * channels * nb, channels * nb, bits))
     body += chunk(b"bext", b"bench.py\0" * 5) + chunk(b"data", pcm) + chunk(b"LIST", b"INFOINAM\x06\0\0\0bench\0")
     return b"RIFF" + struct.pack("<I", 4 + len(body)) + b"WAVE" + body
+
+
+def aiff_file_bytes(pcm: bytes, channels: int, bits: int, rate: int) -> bytes:
+    """A minimal FORM/AIFF (COMM + SSND) around big-endian PCM, with a foreign chunk either side."""
+    def chunk(cid, data):
+        return cid + struct.pack(">I", len(data)) + data + (b"\0" if len(data) & 1 else b"")
+
+    frames = len(pcm) // (channels * bits // 8)
+    m, e = math.frexp(float(rate))                          # 80-bit extended sample rate
+    ext = struct.pack(">HQ", e - 1 + 16383, int(m * (1 << 64)))
+    body = chunk(b"NAME", b"bench.py") + chunk(b"COMM", struct.pack(">hIh", channels, frames, bits) + ext)
+    body += chunk(b"SSND", struct.pack(">II", 0, 0) + pcm) + chunk(b"ANNO", b"after the samples")
+    return b"FORM" + struct.pack(">I", 4 + len(body)) + b"AIFF" + body
+
+
+def cli_single_file(env: Env, cfg: dict) -> dict:
+    """What a `lowcut` user waits for on the headline workload: the shipped C++ host on a tmpfs file
+    of the config's shape, wall clock, with the start-up / filter / write / exit break-down of its -v
+    time stamps -- and its output compared, byte for byte, with what this process's own context makes
+    of the same payload (which the parity block has checked against the oracle)."""
+    import re
+
+    torch, ctx = env.torch, env.ctx
+    lowcut = os.path.join(ROOT, "host", "lowcut")
+    if not os.path.exists(lowcut):
+        return {"ok": False, "error": "host/lowcut is not built"}
+    fs, ch, bits, be, frames = cfg["fs"], cfg["channels"], cfg["bits"], cfg["be"], cfg["frames"]
+    fb = ch * bits // 8
+    d = torch.empty(frames * fb, dtype=torch.uint8, device=env.dev)
+    ctx.synth_pcm_dev(SEED, 0, frames, ch, bits, be, fs, 1.0, d)
+    ctx.synchronize()
+    pcm = d.cpu().numpy()
+    del d
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="lowcut_bench_", dir=base)
+    try:
+        ext = ".aif" if be else ".wav"
+        src, out = os.path.join(tmp, "in" + ext), os.path.join(tmp, "out" + ext)
+        data = aiff_file_bytes(pcm.tobytes(), ch, bits, fs) if be else wav_file_bytes(pcm.tobytes(), ch, bits, fs)
+        open(src, "wb").write(data)
+        args = [lowcut, "-O", "-v", "-f", str(cfg["freq"]), "-s", str(cfg["slope"])] + (["-n"] if cfg["normalize"] else [])
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = subprocess.run(args + [src, out], capture_output=True, text=True, timeout=600)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"ok": False, "error": f"lowcut exit {r.returncode}: {r.stderr[-300:]}"}
+            if best is None or dt < best[0]:
+                best = (dt, r.stdout)
+        wall, text = best
+
+        def stamp(pat):
+            m = re.search(pat, text)
+            return float(m.group(1)) if m else None
+
+        ready = stamp(r"\[\s*([\d.]+) s since start\] \d+ GPU context")
+        done = stamp(r"\[\s*([\d.]+) s since start\] done")
+        filtered = stamp(r"\[\s*([\d.]+) s\] filtered")
+        written = stamp(r"\[\s*([\d.]+) s\] encoded and written")
+        off = data.index(b"SSND") + 16 if be else data.index(b"data") + 8
+        got = open(out, "rb").read()
+        k = ctx.build_kernel(cfg["freq"] / fs, cfg["slope"] / fs)
+        want = np.empty(pcm.size, dtype=np.uint8)
+        ctx.process(k, pcm, frames, ch, bits, be, cfg["normalize"], want)
+        k.free()
+        same = got[off:off + pcm.size] == want.tobytes()
+        meta = got[:off] == data[:off] and got[off + pcm.size:] == data[off + pcm.size:]
+        return {"workload": cfg["name"], "file": f"{len(data) / 1e6:.1f} MB on " + ("tmpfs" if base else "a tmp dir"),
+                "wall_s": wall, "msamples_per_s_wall": frames * ch / wall / 1e6,
+                "start_up_s": ready, "read_upload_filter_s": filtered,
+                "encode_download_write_s": (written - filtered) if written is not None and filtered is not None else None,
+                "exit_s": (wall - done) if done is not None else None,
+                "payload_equals_library": bool(same), "metadata_identical": bool(meta), "ok": bool(same and meta),
+                "what": "best of 3 runs of host/lowcut -v; start_up = exec + CUDA init + context; exit = the driver "
+                        "releasing the context after the output is complete"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def cli_block_identity(env: Env, n_gpus: int) -> dict:
@@ -953,7 +1034,8 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle windows (profiling runs)")
-    ap.add_argument("--no-cli", action="store_true", help="N>1: skip host/lowcut -g N vs -g 1")
+    ap.add_argument("--no-cli", action="store_true", help="skip the host/lowcut runs (N=1: timing + identity on the "
+                                                          "workload's file; N>1: -g N vs -g 1)")
     a = ap.parse_args()
     if a.warmup < 3 and a.config != 6:
         a.warmup = 3 if a.impl == "ours" else a.warmup
@@ -1022,6 +1104,11 @@ def main() -> int:
         else:
             store.wait(["bench_cli_done"])
         env.barrier()
+    if world == 1 and not a.no_cli:
+        try:
+            cli = cli_single_file(env, cfg)
+        except Exception as e:  # noqa: BLE001
+            cli = {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
     line = None
     ok = True
@@ -1037,7 +1124,7 @@ def main() -> int:
         if also:
             line["also"] = also
         if cli is not None:
-            line["cli_block_mode"] = cli
+            line["cli_block_mode" if world > 1 else "cli"] = cli
         ok = (head["parity"] is None or head["parity"]["ok"]) and all(
             v["parity"] is None or v["parity"]["ok"] for v in also.values()) and (cli is None or cli["ok"])
         line["bench_seconds_gpu_arm"] = time.perf_counter() - t_all

@@ -82,7 +82,10 @@ def test_gpu_arm_prints_the_full_contract_line():
     assert p["ok"] is True and p["windows"] >= 4 and p["worst_d3"] <= 1e-12 and p["max_flip_lsb"] <= 1
     assert p["pcm_windows"] >= 2 * p["windows"] and p["global_peak_is_max_of_block_peaks"] is True
     assert d["e2e"]["pipelined"]["matches_serial_arm"] is True and d["e2e"]["copy_ceiling"]["d2h_gbs_per_rank"] > 1
-    assert d["roofline"]["traffic_source"]
+    assert d["roofline"]["traffic_source"] and d["roofline"]["probe_clocks"]["sm_mhz"]
+    c = d["cli"]                                           # the shipped C++ host on the same workload's file
+    assert c["ok"] is True and c["payload_equals_library"] is True and c["metadata_identical"] is True
+    assert 0 < c["wall_s"] < 30 and c["start_up_s"] is not None and c["exit_s"] is not None
     e = d["e2e"]
     assert 0 < e["value"] < d["value"] and e["matches_device_arm"] is True
     assert e["h2d_bytes_per_step"] == 2_880_000 * 6 and e["d2h_bytes_per_step"] == 2_880_000 * 6 + 8
