@@ -26,6 +26,10 @@ big-endian AIFF with ``-f 30 -s 10 -n``):
               random interior positions) against the CPU oracle: the parked FP64 signal
               at the D3 tolerance, the encoded PCM (device arm and host arm) for 1-LSB
               flips, the taps, the peak.  A failure makes the process exit non-zero.
+``cli``     : N=1: the shipped C++ host (host/lowcut) on a tmpfs file of the workload's shape -- wall
+              clock with its start-up / filter / write / exit break-down, output byte-identical to what
+              this process's own context makes of the same payload.  N>1: ``cli_block_mode`` instead
+              (lowcut -g N against -g 1, byte-identical; seam windows against the oracle).
 ``also``    : one record per other BASELINE config (N=1: configs 1, 4, a config-5 slice and
               config 3 IN FULL; N=8: config 3 split into sample blocks), each with its own
               parity block.
