@@ -79,3 +79,44 @@ def test_pcm_struct_layout_matches_header():
     assert ctypes.sizeof(capi.PcmFormat) == 40
     assert capi.PcmFormat.halo_left.offset == 24
     assert ctypes.sizeof(capi.Timing) == 64
+
+
+def test_shipped_cubin_uses_the_hardware_paths_the_design_claims():
+    """cuobjdump of the library that is benchmarked (no GPU needed): the default FIR kernel is the
+    DMMA tensor-path kernel staged by 1-D TMA bulk copies behind mbarriers, with a bounded spin
+    (trap); the product build carries exactly one DMMA and one DFMA FIR shape; the codec kernels
+    convert with a saturating F2I and keep no FP64 min/max sequences (DSETP)."""
+    import shutil
+    import subprocess
+
+    from audio_fir_filter_b200 import capi
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    kernels, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            kernels[cur].append(line)
+    fir = [k for k in kernels if "fir_dmma_kernel" in k]
+    dfma = [k for k in kernels if "fir_fp64_kernel" in k]
+    assert len(fir) == 1 and len(dfma) == 1, (fir, dfma)       # other shapes need -DFIR_ALL_VARIANTS
+    text = "\n".join(kernels[fir[0]])
+    assert text.count("DMMA") >= 128 and "UBLKCP" in text and "SYNCS" in text and "BPT.TRAP" in text
+    assert "DFMA" not in text
+    assert "\n".join(kernels[dfma[0]]).count("DFMA") >= 256 and "UTMALDG" in "\n".join(kernels[dfma[0]])
+    enc = [k for k in kernels if "pcm_encode_kernel" in k]
+    dec = [k for k in kernels if "pcm_decode_kernel" in k]
+    assert len(enc) == 6 and len(dec) == 6                      # 16/24/32 bit x little/big endian
+    for k in enc:
+        t = "\n".join(kernels[k])
+        assert "F2I" in t and "DSETP" not in t, k              # saturating convert, no FP64 min/max sequences
+        assert "LDG.E.NA.128" in t, k                          # read-once planar loads bypass L1 allocation
+        assert "ATOMG.E.ADD" in t, k                           # tiles handed out by the global counter
+    for k in dec:
+        t = "\n".join(kernels[k])
+        assert "STG.E.128" in t and "I2F" in t and "LDG.E.NA.128" in t and "ATOMG.E.ADD" in t, k
