@@ -427,6 +427,31 @@ def peak_hbm() -> float:
         return 6650.0  # B200_PROFILING.md fallback
 
 
+def max_over_ranks(world: int, dev, *vals):
+    """Max over ranks of each value (timings: the slowest rank counts)."""
+    if world == 1:
+        return list(vals)
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def gather_rows(world: int, dev, row):
+    """Every rank's list of floats -> list of lists, rank by rank (on every rank)."""
+    if world == 1:
+        return [list(row)]
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(row), dtype=torch.float64, device=dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [[float(v) for v in o] for o in out]
+
+
 class Env:
     """What every workload of one bench process shares."""
 
@@ -483,20 +508,10 @@ class Env:
             self.torch.cuda.synchronize(self.dev)
 
     def max_over_ranks(self, *vals):
-        if self.world == 1:
-            return list(vals)
-        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return [float(v) for v in t]
+        return max_over_ranks(self.world, self.dev, *vals)
 
     def gather_rows(self, row):
-        """Every rank's list of floats -> list of lists (on every rank)."""
-        if self.world == 1:
-            return [list(row)]
-        t = self.torch.tensor(list(row), dtype=self.torch.float64, device=self.dev)
-        out = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
-        return [[float(v) for v in o] for o in out]
+        return gather_rows(self.world, self.dev, row)
 
     def close(self):
         if self._ctx2 is not None:

@@ -89,3 +89,48 @@ def test_sample_block_mode_over_gloo(tmp_path, oracle_mod, world):
     s.close()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def _bench_worker(rank, world, port, tmp):
+    """bench.py's multi-rank plumbing over gloo: every rank checks the windows of ITS block with the
+    parity checker (an oracle-backed stand-in serves the 'parked signal'), the rows are gathered,
+    timings are max-reduced -- what `bench.py --gpus N` does around the GPU work."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import oracle
+    from test_bench_parity_checker import CFG, FakeCtx, FakeKernel, make_block
+
+    oracle.set_threads(1)
+    taps, blk, y = make_block(oracle, world, rank)
+    if rank == world - 1 and os.path.exists(os.path.join(tmp, "inject")):
+        y = y.copy()
+        y[0, 1] += 1e-9                                   # a defect at the last rank's left seam
+    pw = bench.ParityWindows(CFG, blk, CFG["frames"], bench.SEED, FakeKernel(taps), rank, W=256, n_random=2)
+    pw.check_taps(CFG).check_signal(FakeCtx(y))
+    r = pw.result
+    rows = bench.gather_rows(world, "cpu", [r["windows"], r["worst_d3"], 1.0 if r["ok"] else 0.0, float(np.abs(y).max())])
+    assert len(rows) == world and all(len(x) == 4 for x in rows)
+    assert rows[rank][0] == r["windows"]
+    (slowest,) = bench.max_over_ranks(world, "cpu", float(10 + rank))
+    assert slowest == 10 + world - 1
+    if rank == 0:
+        verdict = all(x[2] == 1.0 for x in rows)
+        open(os.path.join(tmp, "verdict"), "w").write("ok" if verdict else "fail")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("inject", [False, True])
+def test_bench_parity_gather_over_gloo(tmp_path, oracle_mod, inject):
+    if inject:
+        (tmp_path / "inject").write_text("1")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_bench_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "verdict").read_text() == ("fail" if inject else "ok")
