@@ -459,29 +459,6 @@ fir_gpu_ctx* GpuPool::acquire_slot(size_t slot)
 	return l.ctx;
 }
 
-std::vector<fir_gpu_ctx*> GpuPool::acquire_device(size_t device, size_t subs, std::vector<size_t>* slots)
-{
-	device = std::min(device, ordinals_.size() - 1);
-	subs = std::clamp<size_t>(subs, 1, LANES);
-	std::vector<size_t> want;
-	for (size_t sub = 0; sub < subs; ++sub) want.push_back(LANES * device + sub);
-	std::vector<std::thread> th;
-	std::vector<std::string> errs(lanes_.size());
-	for (size_t slot : want)
-		if (!lanes_[slot].ctx)
-			th.emplace_back([this, slot, &errs] {
-				if (fir_gpu_create(ordinals_[slot / LANES], &lanes_[slot].ctx) != FIR_GPU_OK) errs[slot] = fir_gpu_last_error();
-			});
-	for (auto& t : th) t.join();
-	std::vector<fir_gpu_ctx*> out;
-	for (size_t slot : want) {
-		if (!lanes_[slot].ctx) throw GpuError(FIR_GPU_ERR_NO_DEVICE, "cannot create a GPU context: " + errs[slot]);
-		out.push_back(lanes_[slot].ctx);
-	}
-	if (slots) *slots = want;
-	return out;
-}
-
 fir_gpu_kernel* GpuPool::kernel(size_t slot, double fc, double bw, long long* half_len)
 {
 	Lane& l = lanes_.at(slot); // a lane is used by one thread at a time: no lock

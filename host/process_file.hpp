@@ -44,8 +44,6 @@ public:
 	// One lane's context, created by the thread that will use it (batch mode: every lane brings up
 	// its own context and starts on the files at once; the others are still being created).
 	fir_gpu_ctx* acquire_slot(size_t slot);
-	// The lanes of ONE device.
-	std::vector<fir_gpu_ctx*> acquire_device(size_t device, size_t subs, std::vector<size_t>* slots = nullptr);
 	// Two pinned buffers of `bytes` for upload and two for download, per lane, reused across files.
 	unsigned char* staging(size_t slot, int which /*0..3*/, size_t bytes);
 	// The low-cut kernel for (fc, bw) on that lane, built once and kept: files of one batch
